@@ -1,0 +1,148 @@
+/* SharedHeader.h -- the host/device shared records of the ray-cast + radiance path.
+ *
+ * The reference's test/SharedHeader.h:1-3 is an empty shim; the records it was
+ * meant to hold are declared twice there: on the host in
+ * test/RaytraceTest.cpp:50-76 (#pragma pack(1), 64 B each) and again in
+ * test/ClKernels/GenerateColors.cl:12-28.  This header is the single definition
+ * for this repo: byte-identical 64-byte Triangle / Material records (the API
+ * format a caller uploads), plus the B200-side records the BVH path uses
+ * (64-byte two-child node, 48-byte precomputed-edge triangle) and the render
+ * parameter block that replaces the reference's hard-coded constants.
+ *
+ * Plain C (C99) and C++ compatible; no CUDA or torch types.
+ */
+#ifndef PTB200_SHARED_HEADER_H
+#define PTB200_SHARED_HEADER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_DIFFUSE 1  /* GenerateColors.cl:3 */
+#define PTB_SPECULAR 2 /* GenerateColors.cl:4 */
+
+typedef struct ptb_float4 {
+    float x, y, z, w;
+} ptb_float4;
+
+/* RaytraceTest.cpp:9-15 -- the by-value kernel constant {W, H, frame, unused} */
+typedef struct ptb_int4 {
+    int32_t x, y, z, w;
+} ptb_int4;
+
+/* RaytraceTest.cpp:50-59 / GenerateColors.cl:12-19.  Indexed by QUAD id. */
+typedef struct ptb_material {
+    ptb_float4 albedo;   /* 16 */
+    ptb_float4 emissive; /* 16 */
+    float roughness;     /* 4  (GGX alpha, used as-is) */
+    int32_t type;        /* 4  PTB_DIFFUSE | PTB_SPECULAR */
+    char padding[24];
+} ptb_material;
+
+/* RaytraceTest.cpp:61-76 / GenerateColors.cl:21-28.  id = quad id. */
+typedef struct ptb_triangle {
+    ptb_float4 p1; /* 16, w = 0 */
+    ptb_float4 p2; /* 16 */
+    ptb_float4 p3; /* 16 */
+    int32_t id;    /* 4 */
+    char padding[12];
+} ptb_triangle;
+
+/* ---- B200-side records (BUILD-DEFINED; the reference has no BVH) ---------- */
+
+/* One internal BVH node = 4 x 128-bit words, 64-byte aligned.  It holds the
+ * (padded) boxes of BOTH children, so one coalesced 64-byte fetch decides both
+ * descents.  Child reference: >= 0 internal node index; < 0 leaf, decoded as
+ * first = (~ref) >> 3, count = ((~ref) & 7) + 1 into the ordered triangle
+ * array; PTB_BVH_EMPTY = no child.                                            */
+typedef struct ptb_bvh_node {
+    float lo0[3];
+    int32_t child0; /* word 0: child-0 box min, child-0 ref */
+    float hi0[3];
+    int32_t child1; /* word 1: child-0 box max, child-1 ref */
+    float lo1[3];
+    int32_t pad0; /* word 2: child-1 box min */
+    float hi1[3];
+    int32_t pad1; /* word 3: child-1 box max */
+} ptb_bvh_node;
+
+#define PTB_BVH_EMPTY 0x7fffffff
+#define PTB_BVH_LEAF_REF(first, count) (~(int32_t)(((uint32_t)(first) << 3) | (uint32_t)((count)-1)))
+#define PTB_BVH_LEAF_FIRST(ref) ((int32_t)((uint32_t)(~(ref)) >> 3))
+#define PTB_BVH_LEAF_COUNT(ref) ((int32_t)(((uint32_t)(~(ref))) & 7u) + 1)
+#define PTB_BVH_MAX_LEAF 8
+
+/* Triangle in BVH order, precomputed-edge layout: e1 = p2 - p1 and e2 = p3 - p1
+ * are the very fp32 subtractions GenerateColors.cl:92-93 performs per test, only
+ * hoisted, so Moller-Trumbore stays bit-identical.  3 x 128-bit words.         */
+typedef struct ptb_bvh_tri {
+    float p1[3];
+    int32_t index; /* position in the caller's Triangle array (tie-break key) */
+    float e1[3];
+    int32_t quad; /* Triangle.id */
+    float e2[3];
+    int32_t pad;
+} ptb_bvh_tri;
+
+/* ---- render parameters ---------------------------------------------------- */
+
+enum {
+    PTB_MODE_PRIMARY = 0, /* C1: primary ray, hit-ID outputs                          */
+    PTB_MODE_AO = 1,      /* C2: primary + ao_samples cosine-hemisphere any-hit rays   */
+    PTB_MODE_DIRECT = 2,  /* C3: primary + 1 shadow ray to the area light             */
+    PTB_MODE_PATH = 3     /* C4/C5: GenerateColors.cl:223-261 traceRays                */
+};
+enum {
+    PTB_ACCUM_REFERENCE = 0, /* GenerateColors.cl:314-321 gamma-space running mean      */
+    PTB_ACCUM_LINEAR = 1     /* fp32 sum in frame order, divided by n_frames at resolve */
+};
+enum { PTB_INTEGRATOR_AUTO = 0, PTB_INTEGRATOR_MEGAKERNEL = 1, PTB_INTEGRATOR_WAVEFRONT = 2 };
+enum { PTB_ACCEL_BVH = 0, PTB_ACCEL_BRUTE = 1 };
+
+/* Defaults (ptb_render_params_default) equal the reference's hard-coded values:
+ * 512x512 (RaytraceTest.cpp:219), BOUNCES 16 (GenerateColors.cl:5), frame
+ * protocol RaytraceTest.cpp:250-253.                                          */
+typedef struct ptb_render_params {
+    int32_t width, height;
+    int32_t first_frame, n_frames; /* frames first_frame .. first_frame+n_frames-1 */
+    int32_t mode;                  /* PTB_MODE_*        */
+    int32_t accum;                 /* PTB_ACCUM_*       */
+    int32_t integrator;            /* PTB_INTEGRATOR_*  */
+    int32_t accel;                 /* PTB_ACCEL_*       */
+    int32_t max_depth;             /* path segments, reference 16 */
+    int32_t ao_samples;            /* AO rays per primary hit, C2: 16 */
+    float ao_max_dist;             /* AO any-hit tmax */
+    int32_t light_quad;            /* quad id of the area light (cornellbox: 5) */
+    /* image sharding: this call renders the pixels gid with
+     * (gid / shard_block) % shard_count == shard_index; outputs are compacted
+     * to local index (gid / (shard_block*shard_count))*shard_block + gid % shard_block */
+    int32_t shard_index, shard_count, shard_block;
+    int32_t collect_stats; /* 1: fill per-pixel hit-ID / visit outputs and counters */
+    int32_t frames_per_batch; /* wavefront: samples kept in flight; 0 = auto */
+    int32_t reserved[7];
+} ptb_render_params;
+
+/* Ray/test counters (exact integers).  Rays = scene queries (closest or any).
+ * Stage counters feed SURVEY.md 8(d)'s flops/bytes-per-ray formula.           */
+typedef struct ptb_counters {
+    uint64_t rays_closest; /* closest-hit queries */
+    uint64_t rays_any;     /* any-hit (shadow / AO) queries */
+    uint64_t nodes;        /* internal BVH node records fetched (2 slab tests each) */
+    uint64_t tri_tests;    /* Moller-Trumbore tests started (det stage) */
+    uint64_t samples;      /* pixel-frames */
+    uint64_t reserved[3];
+} ptb_counters;
+
+#ifdef __cplusplus
+} /* extern "C" */
+#if __cplusplus >= 201103L
+static_assert(sizeof(ptb_material) == 64, "Material must be 64 bytes (RaytraceTest.cpp:50-59)");
+static_assert(sizeof(ptb_triangle) == 64, "Triangle must be 64 bytes (RaytraceTest.cpp:61-76)");
+static_assert(sizeof(ptb_bvh_node) == 64, "BVH node must be 64 bytes");
+static_assert(sizeof(ptb_bvh_tri) == 48, "BVH triangle must be 48 bytes");
+#endif
+#endif
+
+#endif /* PTB200_SHARED_HEADER_H */
