@@ -115,6 +115,9 @@ typedef struct ptb_render_params {
     int32_t ao_samples;            /* AO rays per primary hit, C2: 16 */
     float ao_max_dist;             /* AO any-hit tmax */
     int32_t light_quad;            /* quad id of the area light (cornellbox: 5) */
+    /* area-light parallelogram P = p1 + xi1*ea + xi2*eb; all-zero ea = derive it
+     * from the first triangle pair whose id is light_quad                        */
+    float light_p1[3], light_ea[3], light_eb[3];
     /* image sharding: this call renders the pixels gid with
      * (gid / shard_block) % shard_count == shard_index; outputs are compacted
      * to local index (gid / (shard_block*shard_count))*shard_block + gid % shard_block */

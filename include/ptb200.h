@@ -1,0 +1,173 @@
+/* ptb200.h -- C-ABI of libptb200.so: the B200-native drop-in for the ray-cast +
+ * radiance-integration path of OclPathTracer.
+ *
+ * The reference drives this path through ADL's header-template C++ API
+ * (adl::DeviceUtils / Buffer<T> / Launcher, no ABI of its own).  Every entry
+ * point below names the ADL call it replaces (paths relative to the reference
+ * root).  Plain pointers and sizes only; every function returns 0 on success or
+ * a negative PTB_E_* code, and ptb_last_error() holds a thread-local message
+ * (the reference reports nothing in release builds: ADLASSERT expands to
+ * `if(x){}`, Adl/AdlError.h:51).
+ *
+ * Threading: like ADL (one in-order queue per device, Adl/CL/AdlCL.cpp:215) a
+ * ptb_device owns ONE CUDA stream and is single-host-thread.
+ *
+ * There is no CPU fallback: without a CUDA device ptb_device_create fails.
+ */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "SharedHeader.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_OK 0
+#define PTB_E_INVALID -1   /* bad argument */
+#define PTB_E_CUDA -2      /* a CUDA runtime call or kernel launch failed */
+#define PTB_E_NODEVICE -3  /* no usable CUDA device */
+#define PTB_E_IO -4        /* file could not be read / parsed */
+#define PTB_E_NOTFOUND -5  /* unknown kernel name */
+#define PTB_E_NOMEM -6
+
+typedef struct ptb_device ptb_device;
+typedef struct ptb_buffer ptb_buffer;
+typedef struct ptb_kernel ptb_kernel;
+typedef struct ptb_scene ptb_scene;
+
+const char* ptb_last_error(void);
+int ptb_version(void);
+
+/* ---- device: adl::init + DeviceUtils::allocate / deallocate ---------------------
+ * Adl/Adl.h:96,125-126; Adl/Adl.cpp:39-58,160-208.  Like DeviceCL::initialize
+ * (Adl/CL/AdlCL.cpp:154) the index is clamped to the last device.              */
+int ptb_device_count(int* count);
+int ptb_device_create(int device_index, ptb_device** out);
+/* same, but enqueue on a caller-owned cudaStream_t (e.g. torch's current stream) */
+int ptb_device_create_on_stream(int device_index, void* cuda_stream, ptb_device** out);
+int ptb_device_destroy(ptb_device* dev);
+/* DeviceUtils::waitForCompletion(const Device*)  Adl/Adl.h:127, Adl/CL/AdlCL.cpp:282-285 */
+int ptb_device_sync(ptb_device* dev);
+/* Device::getDeviceVersion(char[128])  Adl/Adl.h:164 (names the PPM) */
+int ptb_device_name(ptb_device* dev, char out[128]);
+int ptb_device_sm_count(ptb_device* dev, int* sm_count);
+void* ptb_device_stream(ptb_device* dev);
+
+/* ---- buffers: adl::Buffer<T>  Adl/Adl.h:203-265, Adl/Adl.inl:145-253 ------------
+ * Buffer(device, nElems) -> create(bytes); ~Buffer -> destroy;
+ * write/read (Adl.h:218-220, async on the device queue) -> write/read;
+ * getHostPtr/returnHostPtr (Adl.h:230-232, Adl/CL/AdlCL.inl:434-455: map whole
+ * buffer RW, caller then waits; unmap publishes writes) -> map/unmap.          */
+int ptb_buffer_create(ptb_device* dev, size_t bytes, ptb_buffer** out);
+/* non-owning view of caller-allocated device memory (a torch tensor's storage) */
+int ptb_buffer_wrap(ptb_device* dev, void* device_ptr, size_t bytes, ptb_buffer** out);
+int ptb_buffer_destroy(ptb_buffer* buf);
+int ptb_buffer_write(ptb_buffer* buf, const void* host_src, size_t bytes, size_t dst_offset);
+int ptb_buffer_read(ptb_buffer* buf, void* host_dst, size_t bytes, size_t src_offset);
+int ptb_buffer_map(ptb_buffer* buf, void** host_ptr);
+int ptb_buffer_unmap(ptb_buffer* buf, void* host_ptr);
+int ptb_buffer_clear(ptb_buffer* buf); /* Buffer<T>::clear  Adl/Adl.h:226 */
+void* ptb_buffer_device_ptr(ptb_buffer* buf);
+size_t ptb_buffer_size(ptb_buffer* buf);
+
+/* ---- kernel + launcher -----------------------------------------------------------
+ * Device::getKernel(fileName, funcName)  Adl/Adl.h:166, Adl/CL/AdlCL.cpp:490-493,
+ * KernelManager::query Adl/AdlKernel.cpp:94-224: name -> kernel, cached for the
+ * device's lifetime, NULL when unknown.  Here the table holds AOT-compiled CUDA
+ * entry points; file_name may carry the reference's path
+ * ("../test/ClKernels/GenerateColors") -- only its basename is matched.        */
+int ptb_kernel_get(ptb_device* dev, const char* file_name, const char* func_name, ptb_kernel** out);
+/* the reference's compile-time #defines (GenerateColors.cl:5-6) as run-time
+ * options: "NUM_TRIANGLES" (36), "BOUNCES" (16), "ACCEL" (PTB_ACCEL_*)         */
+int ptb_kernel_set_int(ptb_kernel* k, const char* name, int value);
+/* Launcher::setBuffers + setConst + launch1D  Adl/AdlKernel.h:166-184,
+ * Adl/AdlKernel.inl:179-184, Adl/CL/AdlKernelUtilsCL.cpp:399-500.  Positional:
+ * buffers first, then the by-value constant block.  For "GenerateColors":
+ * bufs = {tBuffer, matBuffer, gDst}, consts = ptb_int4{W, H, frame, -}; one
+ * call = one sample per pixel + the gamma-space running mean
+ * (GenerateColors.cl:302-322).  n_threads must equal W*H (the reference rounds
+ * the grid up to 64 and has no guard; this one guards).                        */
+int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* bufs, int n_bufs, const void* consts,
+                 size_t const_bytes, int n_threads, int local_size);
+
+/* ---- host-side scene helpers: RaytraceTest.cpp:87-198 loadModel -------------------- */
+int ptb_load_model(const char* path, ptb_triangle** tris, int* n_tris, ptb_material** mats, int* n_mats);
+/* BUILD-DEFINED C5 scene: each quad (triangle pair) -> k x k sub-quads */
+int ptb_tessellate(const ptb_triangle* tris, int n_tris, int k, ptb_triangle** out, int* n_out);
+int ptb_light_from_quad(const ptb_triangle* tris, int n_tris, int quad, float p1[3], float ea[3], float eb[3]);
+void ptb_free(void* p);
+/* RaytraceTest.cpp:78-83,:277-287: sqrt, x255, truncate, clamp -> ASCII "P3" */
+int ptb_to_rgb8(const float* rgba, int n_pixels, uint8_t* rgb);
+int ptb_write_ppm(const char* path, const float* rgba, int width, int height);
+
+/* ---- resident scene: triangles re-laid out + BVH (BUILD-DEFINED) --------------------- */
+typedef struct ptb_bvh_params {
+    int32_t max_leaf;   /* 1..8, default 4 */
+    float pad_rel;      /* child boxes are grown by pad_rel * scene diagonal, default 1e-4 */
+    int32_t n_bins;     /* SAH bins, default 16 */
+    int32_t smem_nodes; /* top-of-tree nodes laid out first (BFS) for shared-memory staging, default 1024 */
+    int32_t reserved[4];
+} ptb_bvh_params;
+void ptb_bvh_params_default(ptb_bvh_params* p);
+
+/* host-only build (no device needed): returns malloc'd arrays, release with ptb_free */
+int ptb_bvh_build_host(const ptb_triangle* tris, int n_tris, const ptb_bvh_params* bvh_params, ptb_bvh_node** nodes,
+                       int* n_nodes, int32_t** tri_order, ptb_bvh_tri** ordered_tris, int* depth, int* smem_nodes);
+
+int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats, int n_mats,
+                     const ptb_bvh_params* bvh_params /* NULL = default */, ptb_scene** out);
+int ptb_scene_destroy(ptb_scene* scene);
+int ptb_scene_info(ptb_scene* scene, int* n_nodes, int* n_tris, int* depth, int* smem_nodes);
+/* host copies of the built tree, for structural validation and the oracle */
+int ptb_scene_copy_bvh(ptb_scene* scene, ptb_bvh_node* nodes, int32_t* tri_order);
+
+/* ---- the hot path -------------------------------------------------------------------
+ * per-pixel statistics of the LAST frame of a call (collect_stats = 1)          */
+typedef struct ptb_pixel_stats {
+    int32_t tri;               /* primary hit: index into the caller's triangle array, -1 miss */
+    int32_t quad;              /* primary hit: Triangle.id */
+    uint32_t t_bits;           /* primary hit: bits of t */
+    uint32_t visits_primary;   /* BVH nodes fetched by the primary query */
+    uint32_t visits_secondary; /* ... by every other query of the sample */
+    uint32_t count;            /* AO: unoccluded rays; DIRECT: lit; PATH: segments traced */
+    uint32_t id_hash;          /* h = h*31 + (tri+2) over secondary queries in order */
+    uint32_t tri_tests;        /* Moller-Trumbore tests started by the sample */
+} ptb_pixel_stats;
+
+void ptb_render_params_default(ptb_render_params* p);
+int ptb_render_local_pixels(const ptb_render_params* p);
+
+/* Renders frames [first_frame, first_frame + n_frames) of this shard's pixels.
+ * frame: float4 per local pixel (in/out for PTB_ACCUM_REFERENCE when
+ * first_frame > 0).  stats: ptb_pixel_stats per local pixel or NULL.
+ * counters: host pointer or NULL; when given the call synchronises.
+ * Asynchronous on the device's stream otherwise.                               */
+int ptb_render(ptb_device* dev, ptb_scene* scene, const ptb_render_params* params, ptb_buffer* frame,
+               ptb_buffer* stats, ptb_counters* counters);
+
+/* End-to-end convenience with HOST buffers: uploads the scene records (H2D),
+ * (re)builds the resident scene if the records changed, renders, reads the frame
+ * (and stats) back (D2H) and synchronises.  out_rgba: float4 per local pixel. */
+int ptb_render_host(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats, int n_mats,
+                    const ptb_render_params* params, float* out_rgba, ptb_pixel_stats* out_stats,
+                    ptb_counters* counters);
+
+/* ---- unit access for parity tests -----------------------------------------------------
+ * scene query on caller-supplied rays (host arrays: o, d = 3 floats per ray).   */
+int ptb_trace(ptb_device* dev, ptb_scene* scene, int accel, int any_hit, int n_rays, const float* o,
+              const float* d, const float* tmax, int32_t* out_tri, float* out_t, float* out_u, float* out_v,
+              uint32_t* out_visits, uint32_t* out_tests);
+int ptb_test_sincos(ptb_device* dev, const float* x, int n, float* s, float* c);
+int ptb_test_pow(ptb_device* dev, const float* x, int n, float y, float* out);
+int ptb_test_rng(ptb_device* dev, uint32_t gid, uint32_t frame, int n, uint32_t* states, float* values);
+int ptb_test_camera(ptb_device* dev, int width, int height, int frame, int n, const int32_t* gids, float* o,
+                    float* d, uint32_t* seeds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB200_H */

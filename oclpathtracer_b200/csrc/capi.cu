@@ -1,0 +1,843 @@
+// capi.cu -- the C-ABI of libptb200.so (include/ptb200.h): device, buffers,
+// kernel table + launcher, resident scene, and the render entry points that
+// drive the sm_100a kernels.  Replaces the ADL Device/Buffer/Launcher plumbing
+// (Adl/Adl.h, Adl/AdlKernel.h, Adl/CL/*) for this path.  No CPU fallback.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "host_internal.h"
+#include "pt_kernels.cuh"
+#include "pt_wavefront.cuh"
+
+namespace ptb {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                    \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return ptb::fail(PTB_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+}  // namespace ptb
+
+using namespace ptb;
+
+// ---- objects ----------------------------------------------------------------------------------
+
+struct ptb_device {
+    int index = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaDeviceProp prop{};
+    int live_buffers = 0;
+    // scratch, grown on demand
+    void* samples = nullptr; size_t samples_bytes = 0;
+    void* sum = nullptr; size_t sum_bytes = 0;
+    void* wf = nullptr; size_t wf_bytes = 0;  // wavefront queues
+    unsigned long long* counters = nullptr;   // CTR_COUNT + wavefront queue counters
+    std::map<std::string, ptb_kernel*> kernels;  // KernelManager::m_map analogue (Adl/AdlKernel.cpp:142)
+    // ptb_render_host cache
+    ptb_scene* host_scene = nullptr; uint64_t host_scene_hash = 0;
+    ptb_buffer* host_tris = nullptr; ptb_buffer* host_mats = nullptr;
+    ptb_buffer* host_frame = nullptr; ptb_buffer* host_stats = nullptr;
+    void* pinned = nullptr; size_t pinned_bytes = 0;
+};
+
+struct ptb_buffer {
+    ptb_device* dev = nullptr;
+    void* d_ptr = nullptr;
+    size_t bytes = 0;
+    bool owned = true;
+    void* h_map = nullptr;  // pinned staging for map/unmap
+    uint64_t version = 0;
+};
+
+struct ptb_kernel {
+    std::string name;
+    int num_triangles = 36;  // GenerateColors.cl:6
+    int bounces = 16;        // GenerateColors.cl:5
+    int accel = PTB_ACCEL_BVH;
+    int integrator = PTB_INTEGRATOR_AUTO;
+    // scene cache keyed on the bound buffers
+    ptb_scene* scene = nullptr;
+    const ptb_buffer* key_t = nullptr; const ptb_buffer* key_m = nullptr;
+    uint64_t ver_t = 0, ver_m = 0, hash = 0;
+};
+
+struct ptb_scene {
+    ptb_device* dev = nullptr;
+    BuiltBvh bvh;
+    int n_tris = 0, n_mats = 0;
+    float4* d_nodes = nullptr;
+    float4* d_tris = nullptr;
+    float4* d_tris_orig = nullptr;
+    float4* d_mats = nullptr;
+    bool small = false;
+    std::vector<ptb_triangle> host_tris;  // kept for the default light lookup
+};
+
+static int set_device(ptb_device* dev) {
+    CU_TRY(cudaSetDevice(dev->index));
+    return PTB_OK;
+}
+
+static int ensure(void** p, size_t* cur, size_t want) {
+    if (*cur >= want) return PTB_OK;
+    if (*p) CU_TRY(cudaFree(*p));
+    *p = nullptr; *cur = 0;
+    CU_TRY(cudaMalloc(p, want));
+    *cur = want;
+    return PTB_OK;
+}
+
+// ---- misc ---------------------------------------------------------------------------------------
+
+extern "C" const char* ptb_last_error(void) { return g_err; }
+extern "C" int ptb_version(void) { return 100; }
+
+extern "C" int ptb_device_count(int* count) {
+    if (!count) return fail(PTB_E_INVALID, "ptb_device_count: null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail(PTB_E_NODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *count = n;
+    return PTB_OK;
+}
+
+static int device_create(int device_index, void* stream, bool own, ptb_device** out) {
+    if (!out) return fail(PTB_E_INVALID, "ptb_device_create: null out");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(PTB_E_NODEVICE, "ptb_device_create: no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    if (device_index < 0) device_index = 0;
+    if (device_index > n - 1) device_index = n - 1;  // Adl/CL/AdlCL.cpp:154 clamps the same way
+    ptb_device* d = new ptb_device();
+    d->index = device_index;
+    d->own_stream = own;
+    if (cudaSetDevice(device_index) != cudaSuccess || cudaGetDeviceProperties(&d->prop, device_index) != cudaSuccess) {
+        delete d;
+        return fail(PTB_E_CUDA, "ptb_device_create: cannot select device %d", device_index);
+    }
+    if (d->prop.major < 10) {
+        int code = fail(PTB_E_NODEVICE, "ptb_device_create: device %d is sm_%d%d; kernels are built for sm_100a only",
+                        device_index, d->prop.major, d->prop.minor);
+        delete d;
+        return code;
+    }
+    if (own) {
+        if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete d;
+            return fail(PTB_E_CUDA, "ptb_device_create: cudaStreamCreate failed");
+        }
+    } else {
+        d->stream = static_cast<cudaStream_t>(stream);
+    }
+    if (cudaMalloc(&d->counters, sizeof(unsigned long long) * 64) != cudaSuccess) {
+        delete d;
+        return fail(PTB_E_CUDA, "ptb_device_create: cudaMalloc failed");
+    }
+    cudaMemsetAsync(d->counters, 0, sizeof(unsigned long long) * 64, d->stream);
+    *out = d;
+    return PTB_OK;
+}
+
+extern "C" int ptb_device_create(int device_index, ptb_device** out) { return device_create(device_index, nullptr, true, out); }
+extern "C" int ptb_device_create_on_stream(int device_index, void* cuda_stream, ptb_device** out) {
+    return device_create(device_index, cuda_stream, false, out);
+}
+
+extern "C" int ptb_device_sync(ptb_device* dev) {
+    if (!dev) return fail(PTB_E_INVALID, "ptb_device_sync: null device");
+    if (set_device(dev)) return PTB_E_CUDA;
+    CU_TRY(cudaStreamSynchronize(dev->stream));
+    return PTB_OK;
+}
+
+extern "C" int ptb_device_destroy(ptb_device* dev) {
+    if (!dev) return PTB_OK;
+    set_device(dev);
+    cudaStreamSynchronize(dev->stream);
+    if (dev->host_scene) ptb_scene_destroy(dev->host_scene);
+    for (ptb_buffer* b : {dev->host_tris, dev->host_mats, dev->host_frame, dev->host_stats})
+        if (b) ptb_buffer_destroy(b);
+    for (auto& kv : dev->kernels) {
+        if (kv.second->scene) ptb_scene_destroy(kv.second->scene);
+        delete kv.second;
+    }
+    if (dev->samples) cudaFree(dev->samples);
+    if (dev->sum) cudaFree(dev->sum);
+    if (dev->wf) cudaFree(dev->wf);
+    if (dev->counters) cudaFree(dev->counters);
+    if (dev->pinned) cudaFreeHost(dev->pinned);
+    if (dev->own_stream && dev->stream) cudaStreamDestroy(dev->stream);
+    int leaked = dev->live_buffers;
+    delete dev;
+    // DeviceUtils::deallocate asserts (debug only) that all buffers were freed, Adl/Adl.cpp:204
+    if (leaked) return fail(PTB_E_INVALID, "ptb_device_destroy: %d buffer(s) still alive", leaked);
+    return PTB_OK;
+}
+
+extern "C" int ptb_device_name(ptb_device* dev, char out[128]) {
+    if (!dev || !out) return fail(PTB_E_INVALID, "ptb_device_name: null argument");
+    snprintf(out, 128, "%s sm_%d%d CUDA", dev->prop.name, dev->prop.major, dev->prop.minor);
+    return PTB_OK;
+}
+extern "C" int ptb_device_sm_count(ptb_device* dev, int* sm) {
+    if (!dev || !sm) return fail(PTB_E_INVALID, "ptb_device_sm_count: null argument");
+    *sm = dev->prop.multiProcessorCount;
+    return PTB_OK;
+}
+extern "C" void* ptb_device_stream(ptb_device* dev) { return dev ? (void*)dev->stream : nullptr; }
+
+// ---- buffers --------------------------------------------------------------------------------------
+
+extern "C" int ptb_buffer_create(ptb_device* dev, size_t bytes, ptb_buffer** out) {
+    if (!dev || !out) return fail(PTB_E_INVALID, "ptb_buffer_create: null argument");
+    *out = nullptr;
+    if (set_device(dev)) return PTB_E_CUDA;
+    ptb_buffer* b = new ptb_buffer();
+    b->dev = dev;
+    b->bytes = bytes;
+    cudaError_t e = cudaMalloc(&b->d_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {  // ADL: m_ptr = 0, m_size = 0 + log (Adl/CL/AdlCL.inl:190-197)
+        delete b;
+        return fail(PTB_E_NOMEM, "ptb_buffer_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    dev->live_buffers++;
+    *out = b;
+    return PTB_OK;
+}
+
+extern "C" int ptb_buffer_wrap(ptb_device* dev, void* device_ptr, size_t bytes, ptb_buffer** out) {
+    if (!dev || !out || !device_ptr) return fail(PTB_E_INVALID, "ptb_buffer_wrap: null argument");
+    ptb_buffer* b = new ptb_buffer();
+    b->dev = dev; b->d_ptr = device_ptr; b->bytes = bytes; b->owned = false;
+    dev->live_buffers++;
+    *out = b;
+    return PTB_OK;
+}
+
+extern "C" int ptb_buffer_destroy(ptb_buffer* buf) {
+    if (!buf) return PTB_OK;
+    set_device(buf->dev);
+    if (buf->h_map) cudaFreeHost(buf->h_map);
+    if (buf->owned && buf->d_ptr) {
+        cudaStreamSynchronize(buf->dev->stream);
+        cudaFree(buf->d_ptr);
+    }
+    buf->dev->live_buffers--;
+    delete buf;
+    return PTB_OK;
+}
+
+extern "C" int ptb_buffer_write(ptb_buffer* buf, const void* host_src, size_t bytes, size_t dst_offset) {
+    if (!buf || !host_src) return fail(PTB_E_INVALID, "ptb_buffer_write: null argument");
+    if (dst_offset + bytes > buf->bytes) return fail(PTB_E_INVALID, "ptb_buffer_write: range exceeds buffer");
+    if (set_device(buf->dev)) return PTB_E_CUDA;
+    CU_TRY(cudaMemcpyAsync((char*)buf->d_ptr + dst_offset, host_src, bytes, cudaMemcpyHostToDevice, buf->dev->stream));
+    buf->version++;
+    return PTB_OK;
+}
+
+extern "C" int ptb_buffer_read(ptb_buffer* buf, void* host_dst, size_t bytes, size_t src_offset) {
+    if (!buf || !host_dst) return fail(PTB_E_INVALID, "ptb_buffer_read: null argument");
+    if (src_offset + bytes > buf->bytes) return fail(PTB_E_INVALID, "ptb_buffer_read: range exceeds buffer");
+    if (set_device(buf->dev)) return PTB_E_CUDA;
+    CU_TRY(cudaMemcpyAsync(host_dst, (const char*)buf->d_ptr + src_offset, bytes, cudaMemcpyDeviceToHost, buf->dev->stream));
+    return PTB_OK;
+}
+
+extern "C" int ptb_buffer_map(ptb_buffer* buf, void** host_ptr) {
+    if (!buf || !host_ptr) return fail(PTB_E_INVALID, "ptb_buffer_map: null argument");
+    if (set_device(buf->dev)) return PTB_E_CUDA;
+    if (!buf->h_map) CU_TRY(cudaMallocHost(&buf->h_map, buf->bytes ? buf->bytes : 1));
+    // clEnqueueMapBuffer(non-blocking, READ|WRITE): contents valid after the caller waits
+    CU_TRY(cudaMemcpyAsync(buf->h_map, buf->d_ptr, buf->bytes, cudaMemcpyDeviceToHost, buf->dev->stream));
+    *host_ptr = buf->h_map;
+    return PTB_OK;
+}
+
+extern "C" int ptb_buffer_unmap(ptb_buffer* buf, void* host_ptr) {
+    if (!buf || !host_ptr || host_ptr != buf->h_map) return fail(PTB_E_INVALID, "ptb_buffer_unmap: pointer was not mapped");
+    if (set_device(buf->dev)) return PTB_E_CUDA;
+    CU_TRY(cudaMemcpyAsync(buf->d_ptr, buf->h_map, buf->bytes, cudaMemcpyHostToDevice, buf->dev->stream));
+    buf->version++;
+    return PTB_OK;
+}
+
+extern "C" int ptb_buffer_clear(ptb_buffer* buf) {
+    if (!buf) return fail(PTB_E_INVALID, "ptb_buffer_clear: null");
+    if (set_device(buf->dev)) return PTB_E_CUDA;
+    CU_TRY(cudaMemsetAsync(buf->d_ptr, 0, buf->bytes, buf->dev->stream));
+    buf->version++;
+    return PTB_OK;
+}
+
+extern "C" void* ptb_buffer_device_ptr(ptb_buffer* buf) { return buf ? buf->d_ptr : nullptr; }
+extern "C" size_t ptb_buffer_size(ptb_buffer* buf) { return buf ? buf->bytes : 0; }
+
+// ---- resident scene ---------------------------------------------------------------------------------
+
+extern "C" int ptb_scene_destroy(ptb_scene* s) {
+    if (!s) return PTB_OK;
+    set_device(s->dev);
+    cudaStreamSynchronize(s->dev->stream);
+    for (void* p : {(void*)s->d_nodes, (void*)s->d_tris, (void*)s->d_tris_orig, (void*)s->d_mats})
+        if (p) cudaFree(p);
+    delete s;
+    return PTB_OK;
+}
+
+extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats,
+                                int n_mats, const ptb_bvh_params* bvh_params, ptb_scene** out) {
+    if (!dev || !tris || !mats || !out || n_tris < 1 || n_mats < 1)
+        return fail(PTB_E_INVALID, "ptb_scene_create: bad arguments");
+    *out = nullptr;
+    for (int i = 0; i < n_tris; ++i)
+        if (tris[i].id < 0 || tris[i].id >= n_mats)
+            return fail(PTB_E_INVALID, "ptb_scene_create: triangle %d has id %d outside [0,%d)", i, tris[i].id, n_mats);
+    ptb_bvh_params bp;
+    if (bvh_params) bp = *bvh_params; else ptb_bvh_params_default(&bp);
+    ptb_scene* s = new ptb_scene();
+    s->dev = dev; s->n_tris = n_tris; s->n_mats = n_mats;
+    int rc = build_bvh(tris, n_tris, bp, &s->bvh);
+    if (rc) { delete s; return rc; }
+    s->host_tris.assign(tris, tris + n_tris);
+    std::vector<ptb_bvh_tri> orig;
+    make_edge_tris(tris, n_tris, &orig);
+    std::vector<float4> m(size_t(n_mats) * 2);
+    for (int i = 0; i < n_mats; ++i) {
+        m[2 * i] = make_float4(mats[i].albedo.x, mats[i].albedo.y, mats[i].albedo.z, mats[i].roughness);
+        float tbits;
+        std::memcpy(&tbits, &mats[i].type, 4);
+        m[2 * i + 1] = make_float4(mats[i].emissive.x, mats[i].emissive.y, mats[i].emissive.z, tbits);
+    }
+    const size_t staged = s->bvh.nodes.size() * 64 + size_t(n_tris) * 48 + size_t(n_mats) * 32;
+    s->small = staged <= 32 * 1024 && int(s->bvh.nodes.size()) == s->bvh.smem_nodes;
+    if (set_device(dev)) { delete s; return PTB_E_CUDA; }
+    auto up = [&](float4** d, const void* h, size_t bytes) -> int {
+        CU_TRY(cudaMalloc((void**)d, bytes));
+        CU_TRY(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, dev->stream));
+        return PTB_OK;
+    };
+    if ((rc = up(&s->d_nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * 64)) ||
+        (rc = up(&s->d_tris, s->bvh.tris.data(), s->bvh.tris.size() * 48)) ||
+        (rc = up(&s->d_tris_orig, orig.data(), orig.size() * 48)) || (rc = up(&s->d_mats, m.data(), m.size() * 16))) {
+        ptb_scene_destroy(s);
+        return rc;
+    }
+    // the host vectors `orig` and `m` die at return: finish the copies now
+    CU_TRY(cudaStreamSynchronize(dev->stream));
+    *out = s;
+    return PTB_OK;
+}
+
+extern "C" int ptb_bvh_build_host(const ptb_triangle* tris, int n_tris, const ptb_bvh_params* bvh_params,
+                                  ptb_bvh_node** nodes, int* n_nodes, int32_t** tri_order, ptb_bvh_tri** ordered_tris,
+                                  int* depth, int* smem_nodes) {
+    if (!tris || !nodes || !n_nodes || !tri_order) return fail(PTB_E_INVALID, "ptb_bvh_build_host: null argument");
+    ptb_bvh_params bp;
+    if (bvh_params) bp = *bvh_params; else ptb_bvh_params_default(&bp);
+    BuiltBvh b;
+    if (int rc = build_bvh(tris, n_tris, bp, &b)) return rc;
+    *nodes = static_cast<ptb_bvh_node*>(std::malloc(b.nodes.size() * sizeof(ptb_bvh_node)));
+    *tri_order = static_cast<int32_t*>(std::malloc(b.tri_order.size() * sizeof(int32_t)));
+    if (!*nodes || !*tri_order) return fail(PTB_E_NOMEM, "ptb_bvh_build_host: out of memory");
+    std::memcpy(*nodes, b.nodes.data(), b.nodes.size() * sizeof(ptb_bvh_node));
+    std::memcpy(*tri_order, b.tri_order.data(), b.tri_order.size() * sizeof(int32_t));
+    if (ordered_tris) {
+        *ordered_tris = static_cast<ptb_bvh_tri*>(std::malloc(b.tris.size() * sizeof(ptb_bvh_tri)));
+        if (!*ordered_tris) return fail(PTB_E_NOMEM, "ptb_bvh_build_host: out of memory");
+        std::memcpy(*ordered_tris, b.tris.data(), b.tris.size() * sizeof(ptb_bvh_tri));
+    }
+    *n_nodes = int(b.nodes.size());
+    if (depth) *depth = b.depth;
+    if (smem_nodes) *smem_nodes = b.smem_nodes;
+    return PTB_OK;
+}
+
+extern "C" int ptb_scene_info(ptb_scene* s, int* n_nodes, int* n_tris, int* depth, int* smem_nodes) {
+    if (!s) return fail(PTB_E_INVALID, "ptb_scene_info: null scene");
+    if (n_nodes) *n_nodes = int(s->bvh.nodes.size());
+    if (n_tris) *n_tris = s->n_tris;
+    if (depth) *depth = s->bvh.depth;
+    if (smem_nodes) *smem_nodes = s->bvh.smem_nodes;
+    return PTB_OK;
+}
+
+extern "C" int ptb_scene_copy_bvh(ptb_scene* s, ptb_bvh_node* nodes, int32_t* tri_order) {
+    if (!s) return fail(PTB_E_INVALID, "ptb_scene_copy_bvh: null scene");
+    if (nodes) std::memcpy(nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptb_bvh_node));
+    if (tri_order) std::memcpy(tri_order, s->bvh.tri_order.data(), s->bvh.tri_order.size() * sizeof(int32_t));
+    return PTB_OK;
+}
+
+static ptd::SceneDev scene_dev(const ptb_scene* s) {
+    ptd::SceneDev d;
+    d.nodes = s->d_nodes; d.tris = s->d_tris; d.tris_orig = s->d_tris_orig; d.mats = s->d_mats;
+    d.n_nodes = int(s->bvh.nodes.size()); d.n_tris = s->n_tris; d.n_mats = s->n_mats;
+    d.smem_nodes = s->bvh.smem_nodes;
+    d.small = s->small ? 1 : 0;
+    d.stack_depth = s->bvh.depth + 1;
+    return d;
+}
+
+// ---- launch helpers -----------------------------------------------------------------------------------
+
+template <class K>
+static int set_smem(K kernel, size_t smem) {
+    if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return PTB_OK;
+}
+
+template <int MODE, bool BVH, bool SMALL, bool STATS>
+static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::RenderArgs& a) {
+    const int block = 128;
+    const long long total = (long long)a.frames_in_batch * a.n_local;
+    const unsigned grid = (unsigned)((total + block - 1) / block);
+    const size_t smem = ptd::scene_smem_bytes(sc, BVH, SMALL, block);
+    auto k = ptd::k_mega<MODE, BVH, SMALL, STATS>;
+    if (int rc = set_smem(k, smem)) return rc;
+    k<<<grid, block, smem, dev->stream>>>(sc, a);
+    CU_TRY(cudaGetLastError());
+    return PTB_OK;
+}
+
+template <int MODE>
+static int launch_mega_m(ptb_device* dev, const ptd::SceneDev& sc, const ptd::RenderArgs& a, bool bvh, bool small, bool stats) {
+#define PTB_CASE(B, S, T) if (bvh == B && small == S && stats == T) return launch_mega_t<MODE, B, S, T>(dev, sc, a)
+    PTB_CASE(true, true, false); PTB_CASE(true, true, true); PTB_CASE(true, false, false); PTB_CASE(true, false, true);
+    PTB_CASE(false, true, false); PTB_CASE(false, true, true); PTB_CASE(false, false, false); PTB_CASE(false, false, true);
+#undef PTB_CASE
+    return fail(PTB_E_INVALID, "launch_mega: unreachable");
+}
+
+static int launch_mega(ptb_device* dev, int mode, const ptd::SceneDev& sc, const ptd::RenderArgs& a, bool bvh, bool small, bool stats) {
+    switch (mode) {
+        case PTB_MODE_PRIMARY: return launch_mega_m<PTB_MODE_PRIMARY>(dev, sc, a, bvh, small, stats);
+        case PTB_MODE_AO: return launch_mega_m<PTB_MODE_AO>(dev, sc, a, bvh, small, stats);
+        case PTB_MODE_DIRECT: return launch_mega_m<PTB_MODE_DIRECT>(dev, sc, a, bvh, small, stats);
+        case PTB_MODE_PATH: return launch_mega_m<PTB_MODE_PATH>(dev, sc, a, bvh, small, stats);
+    }
+    return fail(PTB_E_INVALID, "ptb_render: unknown mode %d", mode);
+}
+
+// ---- render ---------------------------------------------------------------------------------------------
+
+extern "C" void ptb_render_params_default(ptb_render_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof *p);
+    p->width = 512; p->height = 512;  // RaytraceTest.cpp:219
+    p->first_frame = 0; p->n_frames = 1;
+    p->mode = PTB_MODE_PATH;
+    p->accum = PTB_ACCUM_REFERENCE;
+    p->integrator = PTB_INTEGRATOR_AUTO;
+    p->accel = PTB_ACCEL_BVH;
+    p->max_depth = 16;  // GenerateColors.cl:5
+    p->ao_samples = 16;
+    p->ao_max_dist = 2.0f;
+    p->light_quad = 5;
+    p->shard_index = 0; p->shard_count = 1; p->shard_block = 64;
+}
+
+extern "C" int ptb_render_local_pixels(const ptb_render_params* p) {
+    if (!p) return 0;
+    const long long n = (long long)p->width * p->height;
+    if (p->shard_count <= 1) return (int)n;
+    long long c = 0;
+    for (long long b = p->shard_index; b * p->shard_block < n; b += p->shard_count) {
+        const long long lo = b * p->shard_block, hi = lo + p->shard_block;
+        c += (hi < n ? hi : n) - lo;
+    }
+    return (int)c;
+}
+
+static int validate(const ptb_render_params* p) {
+    if (!p) return fail(PTB_E_INVALID, "ptb_render: null params");
+    if (p->width <= 0 || p->height <= 0 || (long long)p->width * p->height > (1ll << 30))
+        return fail(PTB_E_INVALID, "ptb_render: bad image size %dx%d", p->width, p->height);
+    if (p->n_frames <= 0 || p->first_frame < 0) return fail(PTB_E_INVALID, "ptb_render: bad frame range");
+    if (p->mode < 0 || p->mode > PTB_MODE_PATH) return fail(PTB_E_INVALID, "ptb_render: bad mode %d", p->mode);
+    if (p->accum != PTB_ACCUM_REFERENCE && p->accum != PTB_ACCUM_LINEAR) return fail(PTB_E_INVALID, "ptb_render: bad accum");
+    if (p->max_depth < 1 || p->max_depth > 4096) return fail(PTB_E_INVALID, "ptb_render: bad max_depth");
+    if (p->mode == PTB_MODE_AO && (p->ao_samples < 1 || p->ao_samples > 4096)) return fail(PTB_E_INVALID, "ptb_render: bad ao_samples");
+    if (p->shard_count > 1 && (p->shard_index < 0 || p->shard_index >= p->shard_count || p->shard_block < 1))
+        return fail(PTB_E_INVALID, "ptb_render: bad shard spec");
+    return PTB_OK;
+}
+
+static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_params* p, float4* d_frame, size_t frame_bytes,
+                       ptb_pixel_stats* d_stats, size_t stats_bytes, ptb_counters* counters) {
+    if (!dev || !scene || !d_frame) return fail(PTB_E_INVALID, "ptb_render: null argument");
+    if (int rc = validate(p)) return rc;
+    if (scene->dev != dev) return fail(PTB_E_INVALID, "ptb_render: scene belongs to another device");
+    if (set_device(dev)) return PTB_E_CUDA;
+    const int n_local = ptb_render_local_pixels(p);
+    if (n_local <= 0) return fail(PTB_E_INVALID, "ptb_render: shard owns no pixels");
+    if (frame_bytes < size_t(n_local) * 16) return fail(PTB_E_INVALID, "ptb_render: frame buffer too small (%zu < %zu)", frame_bytes, size_t(n_local) * 16);
+    if (d_stats && stats_bytes < size_t(n_local) * sizeof(ptb_pixel_stats)) return fail(PTB_E_INVALID, "ptb_render: stats buffer too small");
+    if (p->mode == PTB_MODE_DIRECT && (p->light_quad < 0 || p->light_quad >= scene->n_mats))
+        return fail(PTB_E_INVALID, "ptb_render: light_quad %d out of range", p->light_quad);
+
+    ptd::SceneDev sc = scene_dev(scene);
+    const bool bvh = p->accel == PTB_ACCEL_BVH;
+    const bool stats = p->collect_stats != 0;
+    const bool small = scene->small;
+
+    // batch of frames kept in flight
+    int fpb = p->frames_per_batch;
+    if (fpb <= 0) {
+        const long long target = 4ll << 20;
+        fpb = (int)((target + n_local - 1) / n_local);
+    }
+    if (fpb > p->n_frames) fpb = p->n_frames;
+    if (fpb < 1) fpb = 1;
+    if (int rc = ensure(&dev->samples, &dev->samples_bytes, size_t(fpb) * n_local * 16)) return rc;
+    if (p->accum == PTB_ACCUM_LINEAR)
+        if (int rc = ensure(&dev->sum, &dev->sum_bytes, size_t(n_local) * 16)) return rc;
+    CU_TRY(cudaMemsetAsync(dev->counters, 0, sizeof(unsigned long long) * 64, dev->stream));
+
+    ptd::RenderArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.width = p->width; a.height = p->height;
+    a.n_local = n_local;
+    a.max_depth = p->max_depth; a.ao_samples = p->ao_samples; a.ao_max_dist = p->ao_max_dist;
+    a.light_quad = p->light_quad;
+    const bool have_light = p->light_ea[0] != 0.f || p->light_ea[1] != 0.f || p->light_ea[2] != 0.f;
+    if (have_light) {
+        std::memcpy(a.light_p1, p->light_p1, 12); std::memcpy(a.light_ea, p->light_ea, 12); std::memcpy(a.light_eb, p->light_eb, 12);
+    } else if (p->mode == PTB_MODE_DIRECT) {
+        if (int rc = ptb_light_from_quad(scene->host_tris.data(), scene->n_tris, p->light_quad, a.light_p1, a.light_ea, a.light_eb)) return rc;
+    }
+    a.shard.index = p->shard_index; a.shard.count = p->shard_count < 1 ? 1 : p->shard_count; a.shard.block = p->shard_block < 1 ? 1 : p->shard_block;
+    a.samples = static_cast<float4*>(dev->samples);
+    a.stats = stats ? d_stats : nullptr;
+    a.stats_frame = p->first_frame + p->n_frames - 1;
+    a.counters = dev->counters;
+
+    int integrator = p->integrator;
+    if (integrator == PTB_INTEGRATOR_AUTO) integrator = PTB_INTEGRATOR_MEGAKERNEL;
+
+    for (int f0 = 0; f0 < p->n_frames; f0 += fpb) {
+        const int nb = (p->n_frames - f0 < fpb) ? p->n_frames - f0 : fpb;
+        a.first_frame = p->first_frame + f0;
+        a.frames_in_batch = nb;
+        if (integrator == PTB_INTEGRATOR_WAVEFRONT) {
+            if (int rc = ptd::wavefront_render(dev->stream, &dev->wf, &dev->wf_bytes, dev->counters + ptd::CTR_COUNT, p->mode, sc, a, bvh, small, stats,
+                                               dev->prop.multiProcessorCount))
+                return rc;
+        } else {
+            if (int rc = launch_mega(dev, p->mode, sc, a, bvh, small, stats)) return rc;
+        }
+        ptd::ResolveArgs r;
+        r.samples = a.samples; r.n_local = n_local; r.frames_in_batch = nb; r.first_frame = a.first_frame;
+        r.accum = p->accum; r.first_batch = f0 == 0; r.last_batch = f0 + nb >= p->n_frames;
+        r.total_frames = p->n_frames;
+        r.sum = static_cast<float4*>(dev->sum); r.frame = d_frame;
+        ptd::k_resolve<<<(n_local + 255) / 256, 256, 0, dev->stream>>>(r);
+        CU_TRY(cudaGetLastError());
+    }
+    if (counters) {
+        unsigned long long h[ptd::CTR_COUNT];
+        CU_TRY(cudaMemcpyAsync(h, dev->counters, sizeof h, cudaMemcpyDeviceToHost, dev->stream));
+        CU_TRY(cudaStreamSynchronize(dev->stream));
+        std::memset(counters, 0, sizeof *counters);
+        counters->rays_closest = h[ptd::CTR_CLOSEST]; counters->rays_any = h[ptd::CTR_ANY];
+        counters->nodes = h[ptd::CTR_NODES]; counters->tri_tests = h[ptd::CTR_TESTS];
+        counters->samples = (uint64_t)n_local * (uint64_t)p->n_frames;
+    }
+    return PTB_OK;
+}
+
+extern "C" int ptb_render(ptb_device* dev, ptb_scene* scene, const ptb_render_params* params, ptb_buffer* frame,
+                          ptb_buffer* stats, ptb_counters* counters) {
+    if (!frame) return fail(PTB_E_INVALID, "ptb_render: null frame buffer");
+    return render_impl(dev, scene, params, static_cast<float4*>(frame->d_ptr), frame->bytes,
+                       stats ? static_cast<ptb_pixel_stats*>(stats->d_ptr) : nullptr, stats ? stats->bytes : 0, counters);
+}
+
+static uint64_t fnv1a(const void* p, size_t n, uint64_t h) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+static int ensure_buffer(ptb_device* dev, ptb_buffer** b, size_t bytes) {
+    if (*b && (*b)->bytes >= bytes) return PTB_OK;
+    if (*b) ptb_buffer_destroy(*b);
+    *b = nullptr;
+    return ptb_buffer_create(dev, bytes, b);
+}
+
+extern "C" int ptb_render_host(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats,
+                               int n_mats, const ptb_render_params* params, float* out_rgba,
+                               ptb_pixel_stats* out_stats, ptb_counters* counters) {
+    if (!dev || !tris || !mats || !out_rgba) return fail(PTB_E_INVALID, "ptb_render_host: null argument");
+    if (int rc = validate(params)) return rc;
+    if (set_device(dev)) return PTB_E_CUDA;
+    const int n_local = ptb_render_local_pixels(params);
+    const size_t tb = size_t(n_tris) * sizeof(ptb_triangle), mb = size_t(n_mats) * sizeof(ptb_material);
+    const size_t fb = size_t(n_local) * 16, sb = out_stats ? size_t(n_local) * sizeof(ptb_pixel_stats) : 0;
+    // 1. H2D: the caller's records, as the reference flow uploads tBuffer / materialBuffer (RaytraceTest.cpp:222-246)
+    int rc;
+    if ((rc = ensure_buffer(dev, &dev->host_tris, tb)) || (rc = ensure_buffer(dev, &dev->host_mats, mb)) ||
+        (rc = ensure_buffer(dev, &dev->host_frame, fb)) || (sb && (rc = ensure_buffer(dev, &dev->host_stats, sb))))
+        return rc;
+    if (dev->pinned_bytes < tb + mb + fb + sb) {
+        if (dev->pinned) cudaFreeHost(dev->pinned);
+        dev->pinned = nullptr; dev->pinned_bytes = 0;
+        CU_TRY(cudaMallocHost(&dev->pinned, tb + mb + fb + sb));
+        dev->pinned_bytes = tb + mb + fb + sb;
+    }
+    char* pin = static_cast<char*>(dev->pinned);
+    std::memcpy(pin, tris, tb);
+    std::memcpy(pin + tb, mats, mb);
+    if ((rc = ptb_buffer_write(dev->host_tris, pin, tb, 0)) || (rc = ptb_buffer_write(dev->host_mats, pin + tb, mb, 0))) return rc;
+    // 2. resident scene (BVH + relaid records) is rebuilt only when the records changed
+    uint64_t h = fnv1a(tris, tb, 1469598103934665603ull);
+    h = fnv1a(mats, mb, h);
+    if (!dev->host_scene || dev->host_scene_hash != h) {
+        if (dev->host_scene) ptb_scene_destroy(dev->host_scene);
+        dev->host_scene = nullptr;
+        if ((rc = ptb_scene_create(dev, tris, n_tris, mats, n_mats, nullptr, &dev->host_scene))) return rc;
+        dev->host_scene_hash = h;
+    }
+    // 3. in/out frame state for the reference accumulation
+    if (params->accum == PTB_ACCUM_REFERENCE && params->first_frame > 0) {
+        std::memcpy(pin + tb + mb, out_rgba, fb);
+        if ((rc = ptb_buffer_write(dev->host_frame, pin + tb + mb, fb, 0))) return rc;
+    }
+    // 4. render, 5. D2H
+    if ((rc = render_impl(dev, dev->host_scene, params, static_cast<float4*>(dev->host_frame->d_ptr), dev->host_frame->bytes,
+                          sb ? static_cast<ptb_pixel_stats*>(dev->host_stats->d_ptr) : nullptr, sb ? dev->host_stats->bytes : 0, counters)))
+        return rc;
+    if ((rc = ptb_buffer_read(dev->host_frame, pin + tb + mb, fb, 0))) return rc;
+    if (sb && (rc = ptb_buffer_read(dev->host_stats, pin + tb + mb + fb, sb, 0))) return rc;
+    CU_TRY(cudaStreamSynchronize(dev->stream));
+    std::memcpy(out_rgba, pin + tb + mb, fb);
+    if (sb) std::memcpy(out_stats, pin + tb + mb + fb, sb);
+    return PTB_OK;
+}
+
+// ---- kernel table + launcher (drop-in for Device::getKernel / Launcher) -------------------------------------
+
+static std::string base_name(const char* path) {
+    std::string s = path ? path : "";
+    size_t k = s.find_last_of("/\\");
+    if (k != std::string::npos) s = s.substr(k + 1);
+    if (s.size() > 3 && s.compare(s.size() - 3, 3, ".cl") == 0) s.resize(s.size() - 3);
+    return s;
+}
+
+extern "C" int ptb_kernel_get(ptb_device* dev, const char* file_name, const char* func_name, ptb_kernel** out) {
+    if (!dev || !func_name || !out) return fail(PTB_E_INVALID, "ptb_kernel_get: null argument");
+    *out = nullptr;
+    const std::string file = base_name(file_name);
+    if (std::strcmp(func_name, "GenerateColors") != 0 || (!file.empty() && file != "GenerateColors"))
+        return fail(PTB_E_NOTFOUND, "ptb_kernel_get: no kernel %s in %s (known: GenerateColors)", func_name, file.c_str());
+    const std::string key = file + "::" + func_name;
+    auto it = dev->kernels.find(key);
+    if (it == dev->kernels.end()) {
+        ptb_kernel* k = new ptb_kernel();
+        k->name = func_name;
+        it = dev->kernels.emplace(key, k).first;
+    }
+    *out = it->second;
+    return PTB_OK;
+}
+
+extern "C" int ptb_kernel_set_int(ptb_kernel* k, const char* name, int value) {
+    if (!k || !name) return fail(PTB_E_INVALID, "ptb_kernel_set_int: null argument");
+    if (!std::strcmp(name, "NUM_TRIANGLES")) { if (value < 1) return fail(PTB_E_INVALID, "NUM_TRIANGLES must be >= 1"); k->num_triangles = value; k->key_t = nullptr; }
+    else if (!std::strcmp(name, "BOUNCES")) { if (value < 1) return fail(PTB_E_INVALID, "BOUNCES must be >= 1"); k->bounces = value; }
+    else if (!std::strcmp(name, "ACCEL")) k->accel = value;
+    else if (!std::strcmp(name, "INTEGRATOR")) k->integrator = value;
+    else return fail(PTB_E_NOTFOUND, "ptb_kernel_set_int: unknown option %s", name);
+    return PTB_OK;
+}
+
+extern "C" int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* bufs, int n_bufs, const void* consts,
+                            size_t const_bytes, int n_threads, int local_size) {
+    (void)local_size;  // ADL_DEFAULT_LOCAL_SIZE_1D 64 (Adl/AdlKernel.h:71); the CUDA launch shape is ours
+    if (!dev || !k || !bufs || !consts) return fail(PTB_E_INVALID, "ptb_launch1d: null argument");
+    if (n_bufs != 3 || const_bytes != sizeof(ptb_int4))
+        return fail(PTB_E_INVALID, "ptb_launch1d: GenerateColors takes 3 buffers + one int4 (got %d, %zu B)", n_bufs, const_bytes);
+    ptb_buffer* tb = bufs[0]; ptb_buffer* mb = bufs[1]; ptb_buffer* fb = bufs[2];
+    if (!tb || !mb || !fb) return fail(PTB_E_INVALID, "ptb_launch1d: null buffer");
+    ptb_int4 res;
+    std::memcpy(&res, consts, sizeof res);
+    if (res.x <= 0 || res.y <= 0 || res.z < 0) return fail(PTB_E_INVALID, "ptb_launch1d: bad cRes {%d,%d,%d}", res.x, res.y, res.z);
+    if ((long long)res.x * res.y != n_threads)
+        return fail(PTB_E_INVALID, "ptb_launch1d: n_threads %d != W*H %lld", n_threads, (long long)res.x * res.y);
+    const int nt = k->num_triangles;
+    if (size_t(nt) * sizeof(ptb_triangle) > tb->bytes) return fail(PTB_E_INVALID, "ptb_launch1d: tBuffer holds fewer than NUM_TRIANGLES=%d records", nt);
+    if (set_device(dev)) return PTB_E_CUDA;
+    // resident scene for the bound buffers; rebuilt when their contents changed
+    const bool tracked = tb->owned && mb->owned;
+    if (!k->scene || !tracked || k->key_t != tb || k->key_m != mb || k->ver_t != tb->version || k->ver_m != mb->version) {
+        std::vector<ptb_triangle> ht(nt);
+        CU_TRY(cudaMemcpyAsync(ht.data(), tb->d_ptr, size_t(nt) * sizeof(ptb_triangle), cudaMemcpyDeviceToHost, dev->stream));
+        CU_TRY(cudaStreamSynchronize(dev->stream));
+        int max_id = 0;
+        for (const auto& t : ht) if (t.id > max_id) max_id = t.id;
+        const int nm = max_id + 1;
+        if (max_id < 0 || size_t(nm) * sizeof(ptb_material) > mb->bytes) return fail(PTB_E_INVALID, "ptb_launch1d: matBuffer too small for triangle ids");
+        std::vector<ptb_material> hm(nm);
+        CU_TRY(cudaMemcpyAsync(hm.data(), mb->d_ptr, size_t(nm) * sizeof(ptb_material), cudaMemcpyDeviceToHost, dev->stream));
+        CU_TRY(cudaStreamSynchronize(dev->stream));
+        uint64_t h = fnv1a(ht.data(), ht.size() * sizeof(ptb_triangle), 1469598103934665603ull);
+        h = fnv1a(hm.data(), hm.size() * sizeof(ptb_material), h);
+        if (!k->scene || h != k->hash) {
+            if (k->scene) ptb_scene_destroy(k->scene);
+            k->scene = nullptr;
+            if (int rc = ptb_scene_create(dev, ht.data(), nt, hm.data(), nm, nullptr, &k->scene)) return rc;
+            k->hash = h;
+        }
+        k->key_t = tb; k->key_m = mb; k->ver_t = tb->version; k->ver_m = mb->version;
+    }
+    ptb_render_params p;
+    ptb_render_params_default(&p);
+    p.width = res.x; p.height = res.y;
+    p.first_frame = res.z; p.n_frames = 1;  // RaytraceTest.cpp:252-253: one launch = one frame index
+    p.mode = PTB_MODE_PATH; p.accum = PTB_ACCUM_REFERENCE;
+    p.max_depth = k->bounces; p.accel = k->accel; p.integrator = k->integrator;
+    return render_impl(dev, k->scene, &p, static_cast<float4*>(fb->d_ptr), fb->bytes, nullptr, 0, nullptr);
+}
+
+// ---- unit access for parity tests -----------------------------------------------------------------------------
+
+template <class T>
+struct DevArr {
+    T* p = nullptr;
+    ~DevArr() { if (p) cudaFree(p); }
+    int alloc(size_t n) { CU_TRY(cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T))); return PTB_OK; }
+};
+
+extern "C" int ptb_trace(ptb_device* dev, ptb_scene* scene, int accel, int any_hit, int n_rays, const float* o,
+                         const float* d, const float* tmax, int32_t* out_tri, float* out_t, float* out_u, float* out_v,
+                         uint32_t* out_visits, uint32_t* out_tests) {
+    if (!dev || !scene || !o || !d || !tmax || !out_tri || n_rays < 0) return fail(PTB_E_INVALID, "ptb_trace: bad arguments");
+    if (n_rays == 0) return PTB_OK;
+    if (set_device(dev)) return PTB_E_CUDA;
+    const size_t n = size_t(n_rays);
+    DevArr<float> d_o, d_d, d_tm, d_t, d_u, d_v;
+    DevArr<int> d_tri;
+    DevArr<uint32_t> d_vis, d_tst;
+    int rc;
+    if ((rc = d_o.alloc(3 * n)) || (rc = d_d.alloc(3 * n)) || (rc = d_tm.alloc(n)) || (rc = d_t.alloc(n)) || (rc = d_u.alloc(n)) ||
+        (rc = d_v.alloc(n)) || (rc = d_tri.alloc(n)) || (rc = d_vis.alloc(n)) || (rc = d_tst.alloc(n)))
+        return rc;
+    cudaStream_t st = dev->stream;
+    CU_TRY(cudaMemcpyAsync(d_o.p, o, 12 * n, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_d.p, d, 12 * n, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_tm.p, tmax, 4 * n, cudaMemcpyHostToDevice, st));
+    ptd::SceneDev sc = scene_dev(scene);
+    ptd::TraceArgs a{n_rays, d_o.p, d_d.p, d_tm.p, d_tri.p, d_t.p, d_u.p, d_v.p, d_vis.p, d_tst.p};
+    const bool bvh = accel == PTB_ACCEL_BVH, small = scene->small, any = any_hit != 0;
+    const int block = 128;
+    const unsigned grid = (unsigned)((n + block - 1) / block);
+    const size_t smem = ptd::scene_smem_bytes(sc, bvh, small, block);
+#define PTB_TRACE_CASE(B, A, S)                                                \
+    if (bvh == B && any == A && small == S) {                                  \
+        auto k = ptd::k_trace<B, A, S>;                                        \
+        if ((rc = set_smem(k, smem))) return rc;                               \
+        k<<<grid, block, smem, st>>>(sc, a);                                   \
+    }
+    PTB_TRACE_CASE(true, true, true) PTB_TRACE_CASE(true, true, false) PTB_TRACE_CASE(true, false, true) PTB_TRACE_CASE(true, false, false)
+    PTB_TRACE_CASE(false, true, true) PTB_TRACE_CASE(false, true, false) PTB_TRACE_CASE(false, false, true) PTB_TRACE_CASE(false, false, false)
+#undef PTB_TRACE_CASE
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out_tri, d_tri.p, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (out_t) CU_TRY(cudaMemcpyAsync(out_t, d_t.p, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (out_u) CU_TRY(cudaMemcpyAsync(out_u, d_u.p, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (out_v) CU_TRY(cudaMemcpyAsync(out_v, d_v.p, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (out_visits) CU_TRY(cudaMemcpyAsync(out_visits, d_vis.p, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (out_tests) CU_TRY(cudaMemcpyAsync(out_tests, d_tst.p, 4 * n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return PTB_OK;
+}
+
+extern "C" int ptb_test_sincos(ptb_device* dev, const float* x, int n, float* s, float* c) {
+    if (!dev || !x || !s || !c || n < 0) return fail(PTB_E_INVALID, "ptb_test_sincos: bad arguments");
+    if (n == 0) return PTB_OK;
+    if (set_device(dev)) return PTB_E_CUDA;
+    DevArr<float> dx, ds, dc;
+    int rc;
+    if ((rc = dx.alloc(n)) || (rc = ds.alloc(n)) || (rc = dc.alloc(n))) return rc;
+    CU_TRY(cudaMemcpyAsync(dx.p, x, 4 * size_t(n), cudaMemcpyHostToDevice, dev->stream));
+    ptd::k_test_sincos<<<(n + 255) / 256, 256, 0, dev->stream>>>(dx.p, n, ds.p, dc.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(s, ds.p, 4 * size_t(n), cudaMemcpyDeviceToHost, dev->stream));
+    CU_TRY(cudaMemcpyAsync(c, dc.p, 4 * size_t(n), cudaMemcpyDeviceToHost, dev->stream));
+    CU_TRY(cudaStreamSynchronize(dev->stream));
+    return PTB_OK;
+}
+
+extern "C" int ptb_test_pow(ptb_device* dev, const float* x, int n, float y, float* out) {
+    if (!dev || !x || !out || n < 0) return fail(PTB_E_INVALID, "ptb_test_pow: bad arguments");
+    if (n == 0) return PTB_OK;
+    if (set_device(dev)) return PTB_E_CUDA;
+    DevArr<float> dx, dout;
+    int rc;
+    if ((rc = dx.alloc(n)) || (rc = dout.alloc(n))) return rc;
+    CU_TRY(cudaMemcpyAsync(dx.p, x, 4 * size_t(n), cudaMemcpyHostToDevice, dev->stream));
+    ptd::k_test_pow<<<(n + 255) / 256, 256, 0, dev->stream>>>(dx.p, n, y, dout.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, dout.p, 4 * size_t(n), cudaMemcpyDeviceToHost, dev->stream));
+    CU_TRY(cudaStreamSynchronize(dev->stream));
+    return PTB_OK;
+}
+
+extern "C" int ptb_test_rng(ptb_device* dev, uint32_t gid, uint32_t frame, int n, uint32_t* states, float* values) {
+    if (!dev || !states || !values || n < 0) return fail(PTB_E_INVALID, "ptb_test_rng: bad arguments");
+    if (n == 0) return PTB_OK;
+    if (set_device(dev)) return PTB_E_CUDA;
+    DevArr<uint32_t> ds;
+    DevArr<float> dv;
+    int rc;
+    if ((rc = ds.alloc(n)) || (rc = dv.alloc(n))) return rc;
+    ptd::k_test_rng<<<1, 32, 0, dev->stream>>>(gid, frame, n, ds.p, dv.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(states, ds.p, 4 * size_t(n), cudaMemcpyDeviceToHost, dev->stream));
+    CU_TRY(cudaMemcpyAsync(values, dv.p, 4 * size_t(n), cudaMemcpyDeviceToHost, dev->stream));
+    CU_TRY(cudaStreamSynchronize(dev->stream));
+    return PTB_OK;
+}
+
+extern "C" int ptb_test_camera(ptb_device* dev, int width, int height, int frame, int n, const int32_t* gids, float* o,
+                               float* d, uint32_t* seeds) {
+    if (!dev || !gids || !o || !d || !seeds || n < 0) return fail(PTB_E_INVALID, "ptb_test_camera: bad arguments");
+    if (n == 0) return PTB_OK;
+    if (set_device(dev)) return PTB_E_CUDA;
+    DevArr<int> dg;
+    DevArr<float> d_o, d_d;
+    DevArr<uint32_t> ds;
+    int rc;
+    if ((rc = dg.alloc(n)) || (rc = d_o.alloc(3 * size_t(n))) || (rc = d_d.alloc(3 * size_t(n))) || (rc = ds.alloc(n))) return rc;
+    CU_TRY(cudaMemcpyAsync(dg.p, gids, 4 * size_t(n), cudaMemcpyHostToDevice, dev->stream));
+    ptd::k_test_camera<<<(n + 127) / 128, 128, 0, dev->stream>>>(width, height, frame, n, dg.p, d_o.p, d_d.p, ds.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(o, d_o.p, 12 * size_t(n), cudaMemcpyDeviceToHost, dev->stream));
+    CU_TRY(cudaMemcpyAsync(d, d_d.p, 12 * size_t(n), cudaMemcpyDeviceToHost, dev->stream));
+    CU_TRY(cudaMemcpyAsync(seeds, ds.p, 4 * size_t(n), cudaMemcpyDeviceToHost, dev->stream));
+    CU_TRY(cudaStreamSynchronize(dev->stream));
+    return PTB_OK;
+}

@@ -1,0 +1,464 @@
+// pt_kernels.cuh -- sm_100a kernels of the ray-cast + radiance path.
+//
+//   k_mega<MODE,...>   one thread = one sample (pixel x frame): camera ray, scene
+//                      queries and shading in registers; scene staged in shared
+//                      memory by one TMA bulk copy per CTA.
+//   k_resolve          ordered per-pixel accumulation of a batch of samples
+//                      (GenerateColors.cl:314-321 or linear mean).
+//   k_trace            scene queries on caller-supplied rays (parity tests).
+//   wavefront stages   pt_wavefront.cuh
+#pragma once
+
+#include "pt_device.cuh"
+
+namespace ptd {
+
+// ---- counters ---------------------------------------------------------------------------
+enum { CTR_CLOSEST = 0, CTR_ANY = 1, CTR_NODES = 2, CTR_TESTS = 3, CTR_SAMPLES = 4, CTR_COUNT = 8 };
+
+PTD_FI void flush_counter(unsigned long long* counters, int which, uint32_t v) {
+    const uint32_t total = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && total) atomicAdd(&counters[which], (unsigned long long)total);
+}
+
+// ---- shared-memory staging with the bulk async-copy engine (TMA, 1-D) -------------------
+//
+// layout (16-byte aligned pieces):  [mbarrier 16 B][nodes][triangles][materials][stack_ref][stack_tn]
+
+PTD_FI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+PTD_FI void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(mbar))
+                 : "memory");
+}
+
+template <bool BVH, bool SMALL>
+PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
+    Ctx c;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
+    unsigned char* p = smem + 16;
+    const uint32_t node_bytes = BVH ? (uint32_t)sc.smem_nodes * 64u : 0u;
+    const uint32_t tri_bytes = SMALL ? (uint32_t)sc.n_tris * 48u : 0u;
+    const uint32_t mat_bytes = SMALL ? (uint32_t)sc.n_mats * 32u : 0u;
+    float4* s_nodes = reinterpret_cast<float4*>(p);
+    float4* s_tris = reinterpret_cast<float4*>(p + node_bytes);
+    float4* s_mats = reinterpret_cast<float4*>(p + node_bytes + tri_bytes);
+    unsigned char* s_stack = p + node_bytes + tri_bytes + mat_bytes;
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = node_bytes + tri_bytes + mat_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(total)
+                     : "memory");
+        if (node_bytes) bulk_g2s(s_nodes, sc.nodes, node_bytes, mbar);
+        if (tri_bytes) bulk_g2s(s_tris, BVH ? sc.tris : sc.tris_orig, tri_bytes, mbar);
+        if (mat_bytes) bulk_g2s(s_mats, sc.mats, mat_bytes, mbar);
+    }
+    // every thread waits for phase 0 to complete (bytes landed)
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n"
+                : "=r"(done)
+                : "r"(smem_u32(mbar))
+                : "memory");
+        }
+    }
+    c.s_nodes = s_nodes;
+    c.s_tris = s_tris;
+    c.s_mats = s_mats;
+    c.g_nodes = sc.nodes;
+    c.g_tris = BVH ? sc.tris : sc.tris_orig;
+    c.g_mats = sc.mats;
+    c.stride = blockDim.x;
+    c.stack_ref = reinterpret_cast<int*>(s_stack) + threadIdx.x;
+    c.stack_tn = reinterpret_cast<float*>(s_stack + (size_t)sc.stack_depth * blockDim.x * 4) + threadIdx.x;
+    c.smem_nodes = sc.smem_nodes;
+    c.n_tris = sc.n_tris;
+    return c;
+}
+
+// host helper: bytes of dynamic shared memory for a launch
+static inline size_t scene_smem_bytes(const SceneDev& sc, bool bvh, bool small, int block) {
+    size_t b = 16;
+    if (bvh) b += (size_t)sc.smem_nodes * 64;
+    if (small) b += (size_t)sc.n_tris * 48 + (size_t)sc.n_mats * 32;
+    if (bvh) b += (size_t)sc.stack_depth * block * 8;
+    return b;
+}
+
+// ---- per-sample integrators ------------------------------------------------------------------
+
+struct RenderArgs {
+    int width, height;
+    int first_frame;      // frame index of batch slot 0
+    int frames_in_batch;
+    int n_local;          // pixels of this shard
+    int max_depth, ao_samples;
+    float ao_max_dist;
+    int light_quad;
+    float light_p1[3], light_ea[3], light_eb[3];
+    Shard shard;
+    float4* samples;            // [frames_in_batch][n_local] radiance (xyz)
+    ptb_pixel_stats* stats;     // per local pixel, written for stats_frame only
+    int stats_frame;
+    unsigned long long* counters;
+};
+
+template <bool STATS>
+struct SampleStats {
+    int tri, quad;
+    uint32_t t_bits, visits_primary, visits_secondary, count, id_hash, tri_tests;
+};
+template <>
+struct SampleStats<false> {};
+
+template <bool STATS>
+PTD_FI void st_primary(SampleStats<STATS>& st, bool hit, const Hit& h, int quad, uint32_t visits) {
+    if constexpr (STATS) {
+        st.tri = hit ? h.idx : -1;
+        st.quad = hit ? quad : -1;
+        st.t_bits = hit ? __float_as_uint(h.t) : 0u;
+        st.visits_primary = visits;
+    }
+}
+template <bool STATS>
+PTD_FI void st_secondary(SampleStats<STATS>& st, int tri, uint32_t visits) {
+    if constexpr (STATS) {
+        st.visits_secondary += visits;
+        st.id_hash = st.id_hash * 31u + (uint32_t)(tri + 2);
+    }
+}
+
+struct RayCount {
+    uint32_t closest, any;
+};
+
+// GenerateColors.cl:223-261 with BOUNCES -> max_depth
+template <bool BVH, bool SMALL, bool STATS>
+PTD_FI V3 trace_rays(const Ctx& c, Ray r, uint32_t& seed, int max_depth, SampleStats<STATS>& st, RayCount& rc,
+                     QueryStats& qs) {
+    V3 radiance = mk(0.0f, 0.0f, 0.0f);  // :225
+    V3 mask = mk(1.0f, 1.0f, 1.0f);      // :226
+    for (int i = 0; i < max_depth; ++i) {  // :229
+        Hit h;
+        const uint32_t v0 = qs.visits;
+        const bool hit = q_closest<BVH, SMALL, STATS>(c, r.o, r.d, h, qs);
+        rc.closest++;
+        V3 p1, e1, e2; int idx = -1, quad = -1;
+        if (hit) load_tri<SMALL>(c, h.pos, p1, e1, e2, idx, quad);
+        if constexpr (STATS) {
+            if (i == 0) st_primary(st, hit, h, quad, qs.visits - v0);
+            else st_secondary(st, hit ? h.idx : -1, qs.visits - v0);
+            st.count++;
+        }
+        if (!hit) {  // :233-237, max(bg, 0) = bg
+            radiance = mk(radiance.x + mask.x * 0.45f, radiance.y + mask.y * 0.45f, radiance.z + mask.z * 0.45f);
+            break;
+        }
+        V3 p, n;
+        hit_point_normal(e1, e2, r.o, r.d, h, p, n);
+        V3 albedo, emissive; float roughness; int type;
+        load_mat<SMALL>(c, quad, albedo, roughness, emissive, type);  // :239
+        radiance = mk(radiance.x + mask.x * emissive.x * 3.0f, radiance.y + mask.y * emissive.y * 3.0f,
+                      radiance.z + mask.z * emissive.z * 3.0f);      // :241
+        n = dot(n, r.d) < 0.0f ? n : mul(n, -1.0f);                   // :243
+        V3 wi = mk(0.0f, 0.0f, 0.0f);
+        const V3 wo = neg(r.d);                                       // :246
+        float pdf = 0.0f;                                             // :247
+        const V3 color = brdf(wo, wi, pdf, n, albedo, roughness, type, seed);  // :249
+        if (pdf <= 0.0f) break;                                       // :251
+        const float dw = dot(wi, n);
+        mask = mk(mask.x * (color.x * dw / pdf), mask.y * (color.y * dw / pdf), mask.z * (color.z * dw / pdf));  // :253-255
+        r = get_ray(add(p, mul(wi, 0.01f)), wi);                      // :257
+    }
+    return mk(cl_max(radiance.x, 0.0f), cl_max(radiance.y, 0.0f), cl_max(radiance.z, 0.0f));  // :260
+}
+
+// BUILD-DEFINED C1
+template <bool BVH, bool SMALL, bool STATS>
+PTD_FI V3 sample_primary(const Ctx& c, Ray r, SampleStats<STATS>& st, RayCount& rc, QueryStats& qs) {
+    Hit h;
+    const bool hit = q_closest<BVH, SMALL, STATS>(c, r.o, r.d, h, qs);
+    rc.closest++;
+    V3 p1, e1, e2; int idx = -1, quad = -1;
+    if (hit) load_tri<SMALL>(c, h.pos, p1, e1, e2, idx, quad);
+    st_primary(st, hit, h, quad, qs.visits);
+    if constexpr (STATS) st.count = 1;
+    if (!hit) return mk(0.45f, 0.45f, 0.45f);
+    V3 albedo, emissive; float roughness; int type;
+    load_mat<SMALL>(c, quad, albedo, roughness, emissive, type);
+    return albedo;
+}
+
+// BUILD-DEFINED C2
+template <bool BVH, bool SMALL, bool STATS>
+PTD_FI V3 sample_ao(const Ctx& c, Ray r, uint32_t& seed, int ns, float max_dist, SampleStats<STATS>& st,
+                    RayCount& rc, QueryStats& qs) {
+    Hit h;
+    const bool hit = q_closest<BVH, SMALL, STATS>(c, r.o, r.d, h, qs);
+    rc.closest++;
+    V3 p1, e1, e2; int idx = -1, quad = -1;
+    if (hit) load_tri<SMALL>(c, h.pos, p1, e1, e2, idx, quad);
+    st_primary(st, hit, h, quad, qs.visits);
+    if (!hit) return mk(1.0f, 1.0f, 1.0f);
+    V3 p, n;
+    hit_point_normal(e1, e2, r.o, r.d, h, p, n);
+    n = dot(n, r.d) < 0.0f ? n : mul(n, -1.0f);
+    uint32_t open = 0;
+    for (int k = 0; k < ns; ++k) {
+        const V3 wi = sample_hemisphere_cosine(n, seed);
+        const Ray s = get_ray(add(p, mul(wi, 0.01f)), wi);
+        Hit b;
+        const uint32_t v0 = qs.visits;
+        const bool occ = q_any<BVH, SMALL, STATS>(c, s.o, s.d, max_dist, b, qs);
+        rc.any++;
+        st_secondary(st, occ ? b.idx : -1, qs.visits - v0);
+        if (!occ) open++;
+    }
+    if constexpr (STATS) st.count = open;
+    const float v = (float)open / (float)ns;
+    return mk(v, v, v);
+}
+
+// BUILD-DEFINED C3
+template <bool BVH, bool SMALL, bool STATS>
+PTD_FI V3 sample_direct(const Ctx& c, const RenderArgs& a, Ray r, uint32_t& seed, SampleStats<STATS>& st,
+                        RayCount& rc, QueryStats& qs) {
+    Hit h;
+    const bool hit = q_closest<BVH, SMALL, STATS>(c, r.o, r.d, h, qs);
+    rc.closest++;
+    V3 p1, e1, e2; int idx = -1, quad = -1;
+    if (hit) load_tri<SMALL>(c, h.pos, p1, e1, e2, idx, quad);
+    st_primary(st, hit, h, quad, qs.visits);
+    if (!hit) return mk(0.45f, 0.45f, 0.45f);
+    V3 albedo, emissive; float roughness; int type;
+    load_mat<SMALL>(c, quad, albedo, roughness, emissive, type);
+    V3 p, n;
+    hit_point_normal(e1, e2, r.o, r.d, h, p, n);
+    V3 col = mk(1.0f * emissive.x * 3.0f, 1.0f * emissive.y * 3.0f, 1.0f * emissive.z * 3.0f);
+    n = dot(n, r.d) < 0.0f ? n : mul(n, -1.0f);
+    const V3 wo = neg(r.d);
+    const float xi1 = random_float(seed);
+    const float xi2 = random_float(seed);
+    const V3 lp = mk(a.light_p1[0], a.light_p1[1], a.light_p1[2]);
+    const V3 ea = mk(a.light_ea[0], a.light_ea[1], a.light_ea[2]);
+    const V3 eb = mk(a.light_eb[0], a.light_eb[1], a.light_eb[2]);
+    const V3 P = add(add(lp, mul(ea, xi1)), mul(eb, xi2));
+    const V3 L = sub(P, p);
+    const float dist2 = dot(L, L);
+    const float dist = sqrtf(dist2);
+    const V3 wi = normalize(L);
+    const V3 lc = cross(ea, eb);
+    const float area = sqrtf(dot(lc, lc));
+    const V3 nl = normalize(lc);
+    const float cos_s = dot(wi, n);
+    const float cos_l = -dot(wi, nl);
+    if (cos_s > 0.0f && cos_l > 0.0f) {
+        const Ray s = get_ray(add(p, mul(wi, 0.01f)), wi);
+        Hit b;
+        const uint32_t v0 = qs.visits;
+        const bool occ = q_any<BVH, SMALL, STATS>(c, s.o, s.d, dist - 0.02f, b, qs);
+        rc.any++;
+        st_secondary(st, occ ? b.idx : -1, qs.visits - v0);
+        if (!occ) {
+            if constexpr (STATS) st.count = 1;
+            V3 lalb, lem; float lr; int lt;
+            load_mat<SMALL>(c, a.light_quad, lalb, lr, lem, lt);
+            V3 f;
+            if (type == PTB_SPECULAR) {
+                const V3 wh = normalize(add(wo, wi));
+                const float D = distribution_ggx(dot(n, wh), roughness);
+                const float k = D / (4.0f * dot(wi, n) * dot(wo, n));
+                f = mk(k * albedo.x * 2.0f, k * albedo.y * 2.0f, k * albedo.z * 2.0f);
+            } else {
+                f = mul(albedo, PTD_INV_PI);
+            }
+            const float G = cos_s * cos_l / dist2;
+            col = mk(col.x + f.x * (lem.x * 3.0f) * G * area, col.y + f.y * (lem.y * 3.0f) * G * area,
+                     col.z + f.z * (lem.z * 3.0f) * G * area);
+        }
+    }
+    return mk(cl_max(col.x, 0.0f), cl_max(col.y, 0.0f), cl_max(col.z, 0.0f));
+}
+
+// ---- megakernel: one thread per sample ---------------------------------------------------------
+
+template <int MODE, bool BVH, bool SMALL, bool STATS>
+__global__ void __launch_bounds__(128) k_mega(const SceneDev sc, const RenderArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)a.frames_in_batch * a.n_local;
+    RayCount rc{0u, 0u};
+    QueryStats qs{0u, 0u};
+    if (slot < total) {
+        const int fi = (int)(slot / a.n_local);
+        const int li = (int)(slot - (long long)fi * a.n_local);
+        const int gid = gid_of_local(a.shard, li);
+        const int frame = a.first_frame + fi;
+        const int gi = gid % a.width, gj = gid / a.width;           // GenerateColors.cl:305-306
+        uint32_t seed = (uint32_t)gid + hash_uint32((uint32_t)frame);  // :308
+        const Ray r = generate_ray(gi, gj, a.width, a.height, seed);   // :310
+        SampleStats<STATS> st{};
+        V3 col;
+        if (MODE == PTB_MODE_PRIMARY) col = sample_primary<BVH, SMALL, STATS>(c, r, st, rc, qs);
+        else if (MODE == PTB_MODE_AO) col = sample_ao<BVH, SMALL, STATS>(c, r, seed, a.ao_samples, a.ao_max_dist, st, rc, qs);
+        else if (MODE == PTB_MODE_DIRECT) col = sample_direct<BVH, SMALL, STATS>(c, a, r, seed, st, rc, qs);
+        else col = trace_rays<BVH, SMALL, STATS>(c, r, seed, a.max_depth, st, rc, qs);  // :312
+        a.samples[slot] = make_float4(col.x, col.y, col.z, 1.0f);
+        if constexpr (STATS) {
+            if (a.stats && frame == a.stats_frame) {
+                ptb_pixel_stats ps;
+                ps.tri = st.tri; ps.quad = st.quad; ps.t_bits = st.t_bits;
+                ps.visits_primary = st.visits_primary; ps.visits_secondary = st.visits_secondary;
+                ps.count = st.count; ps.id_hash = st.id_hash; ps.tri_tests = qs.tests;
+                uint4* dst = reinterpret_cast<uint4*>(a.stats + li);
+                dst[0] = make_uint4((uint32_t)ps.tri, (uint32_t)ps.quad, ps.t_bits, ps.visits_primary);
+                dst[1] = make_uint4(ps.visits_secondary, ps.count, ps.id_hash, ps.tri_tests);
+            }
+        }
+    }
+    flush_counter(a.counters, CTR_CLOSEST, rc.closest);
+    flush_counter(a.counters, CTR_ANY, rc.any);
+    if (STATS) {
+        flush_counter(a.counters, CTR_NODES, qs.visits);
+        flush_counter(a.counters, CTR_TESTS, qs.tests);
+    }
+}
+
+// ---- ordered accumulation of a batch: GenerateColors.cl:290-321 --------------------------------
+
+PTD_FI V3 gamma_correct(V3 v) {  // :290-294
+    const float g = 1.0f / 2.2f;
+    return mk(det_pow(v.x, g), det_pow(v.y, g), det_pow(v.z, g));
+}
+PTD_FI V3 read_from_gamma(V3 v) {  // :296-300
+    return mk(det_pow(v.x, 2.2f), det_pow(v.y, 2.2f), det_pow(v.z, 2.2f));
+}
+
+struct ResolveArgs {
+    const float4* samples;
+    int n_local, frames_in_batch, first_frame;
+    int accum;
+    int first_batch, last_batch;
+    int total_frames;
+    float4* sum;    // linear running sum (xyz)
+    float4* frame;  // output / gamma-space state
+};
+
+__global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= a.n_local) return;
+    if (a.accum == PTB_ACCUM_REFERENCE) {
+        float4 cur = a.frame[li];
+        V3 state = xyz(cur);
+        float w = cur.w;
+        for (int fi = 0; fi < a.frames_in_batch; ++fi) {
+            const V3 col = xyz(a.samples[(size_t)fi * a.n_local + li]);
+            const int f = a.first_frame + fi;
+            if (f == 0) {  // :314-317
+                state = gamma_correct(col);
+            } else {       // :318-321
+                const V3 prev = read_from_gamma(state);
+                const float zm1 = (float)(f - 1), z = (float)f;
+                state = gamma_correct(mk((prev.x * zm1 + col.x) / z, (prev.y * zm1 + col.y) / z, (prev.z * zm1 + col.z) / z));
+            }
+            w = 1.0f;
+        }
+        a.frame[li] = make_float4(state.x, state.y, state.z, w);
+    } else {
+        V3 s = a.first_batch ? mk(0.0f, 0.0f, 0.0f) : xyz(a.sum[li]);
+        for (int fi = 0; fi < a.frames_in_batch; ++fi) {
+            const V3 col = xyz(a.samples[(size_t)fi * a.n_local + li]);
+            s = mk(s.x + col.x, s.y + col.y, s.z + col.z);
+        }
+        if (a.last_batch) {
+            const float nf = (float)a.total_frames;
+            a.frame[li] = make_float4(s.x / nf, s.y / nf, s.z / nf, 1.0f);
+        } else {
+            a.sum[li] = make_float4(s.x, s.y, s.z, 0.0f);
+        }
+    }
+}
+
+// ---- scene queries on caller-supplied rays (tests) -----------------------------------------------
+
+struct TraceArgs {
+    int n_rays;
+    const float* o;
+    const float* d;
+    const float* tmax;
+    int* out_tri;
+    float* out_t;
+    float* out_u;
+    float* out_v;
+    uint32_t* out_visits;
+    uint32_t* out_tests;
+};
+
+template <bool BVH, bool ANY, bool SMALL>
+__global__ void __launch_bounds__(128) k_trace(const SceneDev sc, const TraceArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_rays) return;
+    const V3 o = mk(a.o[3 * i], a.o[3 * i + 1], a.o[3 * i + 2]);
+    const V3 d = mk(a.d[3 * i], a.d[3 * i + 1], a.d[3 * i + 2]);
+    Hit h;
+    h.t = h.u = h.v = 0.0f; h.pos = h.idx = -1;
+    QueryStats qs{0u, 0u};
+    bool hit;
+    if (ANY) hit = q_any<BVH, SMALL, true>(c, o, d, a.tmax[i], h, qs);
+    else hit = q_closest<BVH, SMALL, true>(c, o, d, h, qs);
+    a.out_tri[i] = hit ? h.idx : -1;
+    a.out_t[i] = hit ? h.t : 0.0f;
+    a.out_u[i] = hit ? h.u : 0.0f;
+    a.out_v[i] = hit ? h.v : 0.0f;
+    a.out_visits[i] = qs.visits;
+    a.out_tests[i] = qs.tests;
+}
+
+// ---- unit kernels for the numerics contract -------------------------------------------------------
+
+__global__ void k_test_sincos(const float* x, int n, float* s, float* c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) det_sincos(x[i], s[i], c[i]);
+}
+__global__ void k_test_pow(const float* x, int n, float y, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = det_pow(x[i], y);
+}
+__global__ void k_test_rng(uint32_t gid, uint32_t frame, int n, uint32_t* states, float* values) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t seed = gid + hash_uint32(frame);
+    for (int i = 0; i < n; ++i) {
+        values[i] = random_float(seed);
+        states[i] = seed;
+    }
+}
+__global__ void k_test_camera(int width, int height, int frame, int n, const int* gids, float* o, float* d,
+                              uint32_t* seeds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int gid = gids[i];
+    uint32_t seed = (uint32_t)gid + hash_uint32((uint32_t)frame);
+    const Ray r = generate_ray(gid % width, gid / width, width, height, seed);
+    o[3 * i] = r.o.x; o[3 * i + 1] = r.o.y; o[3 * i + 2] = r.o.z;
+    d[3 * i] = r.d.x; d[3 * i + 1] = r.d.y; d[3 * i + 2] = r.d.z;
+    seeds[i] = seed;
+}
+
+}  // namespace ptd
