@@ -2,7 +2,7 @@
 
 The product is the C-ABI library (hand-written sm_100a CUDA behind plain-C entry
 points); this module only binds it for the parity tests and bench.py.  It never
-touches oracle/ and has no CPU fallback: a missing library or a failing call
+touches the test oracle and has no CPU fallback: a missing library or a failing call
 raises.
 """
 import ctypes as C

@@ -541,7 +541,7 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
         a.first_frame = p->first_frame + f0;
         a.frames_in_batch = nb;
         if (integrator == PTB_INTEGRATOR_WAVEFRONT) {
-            if (int rc = ptd::wavefront_render(dev->stream, &dev->wf, &dev->wf_bytes, dev->counters + ptd::CTR_COUNT, p->mode, sc, a, bvh, small, stats,
+            if (int rc = ptd::wavefront_render(dev->stream, &dev->wf, &dev->wf_bytes, dev->counters, p->mode, sc, a, bvh, small, stats,
                                                dev->prop.multiProcessorCount))
                 return rc;
         } else {

@@ -34,8 +34,11 @@ PTD_FI void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* mbar) {
                  : "memory");
 }
 
-template <bool BVH, bool SMALL>
+// NODES: stage the node prefix and carve the traversal stack; TRIS_BVH: triangle
+// positions refer to the BVH-ordered array (else the caller-ordered one).
+template <bool NODES, bool SMALL, bool TRIS_BVH = NODES>
 PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
+    constexpr bool BVH = NODES;
     Ctx c;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
     unsigned char* p = smem + 16;
@@ -57,7 +60,7 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(total)
                      : "memory");
         if (node_bytes) bulk_g2s(s_nodes, sc.nodes, node_bytes, mbar);
-        if (tri_bytes) bulk_g2s(s_tris, BVH ? sc.tris : sc.tris_orig, tri_bytes, mbar);
+        if (tri_bytes) bulk_g2s(s_tris, TRIS_BVH ? sc.tris : sc.tris_orig, tri_bytes, mbar);
         if (mat_bytes) bulk_g2s(s_mats, sc.mats, mat_bytes, mbar);
     }
     // every thread waits for phase 0 to complete (bytes landed)
@@ -79,7 +82,7 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
     c.s_tris = s_tris;
     c.s_mats = s_mats;
     c.g_nodes = sc.nodes;
-    c.g_tris = BVH ? sc.tris : sc.tris_orig;
+    c.g_tris = TRIS_BVH ? sc.tris : sc.tris_orig;
     c.g_mats = sc.mats;
     c.stride = blockDim.x;
     c.stack_ref = reinterpret_cast<int*>(s_stack) + threadIdx.x;
@@ -173,6 +176,7 @@ PTD_FI V3 trace_rays(const Ctx& c, Ray r, uint32_t& seed, int max_depth, SampleS
         load_mat<SMALL>(c, quad, albedo, roughness, emissive, type);  // :239
         radiance = mk(radiance.x + mask.x * emissive.x * 3.0f, radiance.y + mask.y * emissive.y * 3.0f,
                       radiance.z + mask.z * emissive.z * 3.0f);      // :241
+        if (i + 1 == max_depth) break;  // the last segment's BSDF sample cannot reach the radiance
         n = dot(n, r.d) < 0.0f ? n : mul(n, -1.0f);                   // :243
         V3 wi = mk(0.0f, 0.0f, 0.0f);
         const V3 wo = neg(r.d);                                       // :246

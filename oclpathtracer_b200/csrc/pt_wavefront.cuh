@@ -1,6 +1,508 @@
-// stub (replaced below)
+// pt_wavefront.cuh -- wavefront integrator: the same per-sample arithmetic as the
+// megakernel (pt_kernels.cuh), split into stages that each run SIMT-dense over a
+// queue of live rays:
+//
+//   wf_generate      camera ray + RNG seed per path slot            (GenerateColors.cl:305-310)
+//   wf_extend        closest-hit scene query per queued ray          (:137-154 / BVH)
+//   wf_shade_*       material, emission, BSDF sample, next ray       (:233-257)
+//                    -> surviving paths are appended to the next queue with
+//                       warp-aggregated atomics (one atomicAdd per warp)
+//   wf_shadow_*      any-hit query per shadow / AO ray
+//   wf_finish_*      per-slot combination of shadow results
+//
+// Queue records are SoA float4 streams (coalesced 128-bit accesses):
+//   q_o = (origin.xyz, slot)  q_d = (dir.xyz, seed)  q_m = (mask.xyz, has_radiance)
+//   hit = (t, u, v, triangle position | -1)
+// A path slot = (frame-in-batch, local pixel); each slot's radiance lands in
+// samples[slot], so k_resolve accumulates in frame order exactly as for the
+// megakernel and both integrators are bit-identical.
 #pragma once
+
+#include "host_internal.h"
 #include "pt_kernels.cuh"
+
 namespace ptd {
-static int wavefront_render(cudaStream_t, void**, size_t*, unsigned long long*, int, const SceneDev&, const RenderArgs&, bool, bool, bool, int) { return -1; }
+
+struct WfBuffers {
+    float4* q_o[2];
+    float4* q_d[2];
+    float4* q_m[2];
+    float4* hit;
+    float4* radiance;        // running radiance of slots that met an emitter and went on
+    float4* slot_p;          // AO: hit point per slot; DIRECT: base colour per slot
+    float4* sq_w;            // AO: (wi.xyz, tmax | <0 hole); DIRECT: (o.xyz, tmax | <0 hole)
+    float4* sq_d;            // DIRECT: (d.xyz, -)
+    float4* sq_c;            // DIRECT: (contribution.xyz, -)
+    int* sq_res;             // per shadow ray: blocker triangle index, -1 = unoccluded, -2 = hole
+    uint32_t* sq_visits;     // STATS
+    uint32_t* sq_tests;      // STATS
+    ptb_pixel_stats* slot_stats;  // STATS: per slot
+    unsigned int* counts;    // queue lengths: counts[d] = rays entering depth d
+};
+
+PTD_FI bool finite3(V3 v) {
+    return fabsf(v.x) <= 3.402823466e38f && fabsf(v.y) <= 3.402823466e38f && fabsf(v.z) <= 3.402823466e38f;
 }
+
+// ---- generate ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wf_generate(const RenderArgs a, const WfBuffers w, const int stats) {
+    const long long total = (long long)a.frames_in_batch * a.n_local;
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot == 0) w.counts[0] = (unsigned int)total;
+    if (slot >= total) return;
+    const int fi = (int)(slot / a.n_local);
+    const int li = (int)(slot - (long long)fi * a.n_local);
+    const int gid = gid_of_local(a.shard, li);
+    const int frame = a.first_frame + fi;
+    uint32_t seed = (uint32_t)gid + hash_uint32((uint32_t)frame);          // GenerateColors.cl:308
+    const Ray r = generate_ray(gid % a.width, gid / a.width, a.width, a.height, seed);  // :310
+    w.q_o[0][slot] = make_float4(r.o.x, r.o.y, r.o.z, __int_as_float((int)slot));
+    w.q_d[0][slot] = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(seed));
+    w.q_m[0][slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    if (stats) {
+        uint4* s = reinterpret_cast<uint4*>(w.slot_stats + slot);
+        s[0] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
+        s[1] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// ---- extend --------------------------------------------------------------------------------------
+template <bool BVH, bool SMALL, bool STATS>
+__global__ void __launch_bounds__(128) wf_extend(const SceneDev sc, const WfBuffers w, const int depth, const int qi,
+                                                 unsigned long long* counters) {
+    const unsigned int n = w.counts[depth];
+    if (blockIdx.x * blockDim.x >= n) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nrays = 0;
+    QueryStats qs{0u, 0u};
+    if (i < n) {
+        const float4 qo = w.q_o[qi][i], qd = w.q_d[qi][i];
+        Hit h;
+        const bool hit = q_closest<BVH, SMALL, STATS>(c, xyz(qo), xyz(qd), h, qs);
+        nrays = 1;
+        w.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(hit ? h.pos : -1));
+        if constexpr (STATS) {
+            ptb_pixel_stats* s = w.slot_stats + __float_as_int(qo.w);
+            if (depth == 0) {
+                int quad = -1;
+                if (hit) {
+                    V3 p1, e1, e2; int idx;
+                    load_tri<SMALL>(c, h.pos, p1, e1, e2, idx, quad);
+                }
+                s->tri = hit ? h.idx : -1;
+                s->quad = quad;
+                s->t_bits = hit ? __float_as_uint(h.t) : 0u;
+                s->visits_primary = qs.visits;
+            } else {
+                s->visits_secondary += qs.visits;
+                s->id_hash = s->id_hash * 31u + (uint32_t)((hit ? h.idx : -1) + 2);
+            }
+            s->tri_tests += qs.tests;
+        }
+    }
+    flush_counter(counters, CTR_CLOSEST, nrays);
+    if (STATS) {
+        flush_counter(counters, CTR_NODES, qs.visits);
+        flush_counter(counters, CTR_TESTS, qs.tests);
+    }
+}
+
+// ---- shade: full path (GenerateColors.cl:233-257) ---------------------------------------------------
+template <bool BVH, bool SMALL, bool STATS>
+__global__ void __launch_bounds__(128) wf_shade_path(const SceneDev sc, const RenderArgs a, const WfBuffers w,
+                                                     const int depth, const int qi) {
+    const unsigned int n = w.counts[depth];
+    if (blockIdx.x * blockDim.x >= n) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Ctx c = stage_scene<false, SMALL, BVH>(sc, smem);  // triangles (in the order extend searched) + materials
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = false;
+    float4 no = make_float4(0, 0, 0, 0), nd = no, nm = no;
+    if (i < n) {
+        const float4 qo = w.q_o[qi][i], qd = w.q_d[qi][i], qm = w.q_m[qi][i];
+        const float4 hr = w.hit[i];
+        const int slot = __float_as_int(qo.w);
+        uint32_t seed = __float_as_uint(qd.w);
+        const V3 o = xyz(qo), d = xyz(qd);
+        V3 mask = xyz(qm);
+        bool has_rad = qm.w != 0.0f;
+        const int pos = __float_as_int(hr.w);
+        if constexpr (STATS) w.slot_stats[slot].count++;
+        V3 add_rad;
+        bool terminate;
+        if (pos < 0) {  // :233-237
+            add_rad = mk(mask.x * 0.45f, mask.y * 0.45f, mask.z * 0.45f);
+            terminate = true;
+        } else {
+            V3 p1, e1, e2; int idx, quad;
+            load_tri<SMALL>(c, pos, p1, e1, e2, idx, quad);
+            Hit h; h.t = hr.x; h.u = hr.y; h.v = hr.z; h.pos = pos; h.idx = idx;
+            V3 p, nrm;
+            hit_point_normal(e1, e2, o, d, h, p, nrm);
+            V3 albedo, emissive; float roughness; int type;
+            load_mat<SMALL>(c, quad, albedo, roughness, emissive, type);                 // :239
+            add_rad = mk(mask.x * emissive.x * 3.0f, mask.y * emissive.y * 3.0f, mask.z * emissive.z * 3.0f);  // :241
+            terminate = depth + 1 >= a.max_depth;  // the last segment's BSDF sample cannot reach the radiance
+            if (!terminate) {
+                nrm = dot(nrm, d) < 0.0f ? nrm : mul(nrm, -1.0f);                       // :243
+                V3 wi = mk(0.0f, 0.0f, 0.0f);
+                const V3 wo = neg(d);                                                    // :246
+                float pdf = 0.0f;
+                const V3 color = brdf(wo, wi, pdf, nrm, albedo, roughness, type, seed);  // :249
+                if (pdf <= 0.0f) {                                                       // :251
+                    terminate = true;
+                } else {
+                    const float dw = dot(wi, nrm);
+                    mask = mk(mask.x * (color.x * dw / pdf), mask.y * (color.y * dw / pdf), mask.z * (color.z * dw / pdf));
+                    const Ray r = get_ray(add(p, mul(wi, 0.01f)), wi);                   // :257
+                    no = make_float4(r.o.x, r.o.y, r.o.z, qo.w);
+                    nd = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(seed));
+                    alive = true;
+                }
+            }
+            // radiance + (+0) is the identity unless the mask is non-finite (0 * inf = NaN)
+            const bool adds = emissive.x != 0.0f || emissive.y != 0.0f || emissive.z != 0.0f || !finite3(xyz(qm));
+            if (!terminate && adds) {
+                V3 rad = has_rad ? xyz(w.radiance[slot]) : mk(0.0f, 0.0f, 0.0f);
+                rad = mk(rad.x + add_rad.x, rad.y + add_rad.y, rad.z + add_rad.z);
+                w.radiance[slot] = make_float4(rad.x, rad.y, rad.z, 0.0f);
+                has_rad = true;
+            }
+        }
+        if (terminate) {
+            V3 rad = has_rad ? xyz(w.radiance[slot]) : mk(0.0f, 0.0f, 0.0f);
+            rad = mk(rad.x + add_rad.x, rad.y + add_rad.y, rad.z + add_rad.z);
+            a.samples[slot] = make_float4(cl_max(rad.x, 0.0f), cl_max(rad.y, 0.0f), cl_max(rad.z, 0.0f), 1.0f);  // :260
+        }
+        nm = make_float4(mask.x, mask.y, mask.z, has_rad ? 1.0f : 0.0f);
+    }
+    // warp-aggregated append to the next queue
+    const unsigned int ballot = __ballot_sync(0xffffffffu, alive);
+    if (ballot) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(ballot) - 1;
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(&w.counts[depth + 1], (unsigned int)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (alive) {
+            const unsigned int dst = base + __popc(ballot & ((1u << lane) - 1u));
+            w.q_o[qi ^ 1][dst] = no;
+            w.q_d[qi ^ 1][dst] = nd;
+            w.q_m[qi ^ 1][dst] = nm;
+        }
+    }
+}
+
+// ---- shade: primary / AO / direct -------------------------------------------------------------------
+template <int MODE, bool BVH, bool SMALL, bool STATS>
+__global__ void __launch_bounds__(128) wf_shade_first(const SceneDev sc, const RenderArgs a, const WfBuffers w) {
+    const unsigned int n = w.counts[0];
+    if (blockIdx.x * blockDim.x >= n) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Ctx c = stage_scene<false, SMALL, BVH>(sc, smem);
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 qo = w.q_o[0][i], qd = w.q_d[0][i];
+    const float4 hr = w.hit[i];
+    const int slot = __float_as_int(qo.w);
+    const long long P = (long long)a.frames_in_batch * a.n_local;
+    uint32_t seed = __float_as_uint(qd.w);
+    const V3 o = xyz(qo), d = xyz(qd);
+    const int pos = __float_as_int(hr.w);
+    if (MODE == PTB_MODE_PRIMARY) {
+        if constexpr (STATS) w.slot_stats[slot].count = 1;
+        if (pos < 0) { a.samples[slot] = make_float4(0.45f, 0.45f, 0.45f, 1.0f); return; }
+        V3 p1, e1, e2; int idx, quad;
+        load_tri<SMALL>(c, pos, p1, e1, e2, idx, quad);
+        V3 albedo, emissive; float roughness; int type;
+        load_mat<SMALL>(c, quad, albedo, roughness, emissive, type);
+        a.samples[slot] = make_float4(albedo.x, albedo.y, albedo.z, 1.0f);
+        return;
+    }
+    if (MODE == PTB_MODE_AO) {
+        const int ns = a.ao_samples;
+        if (pos < 0) {
+            a.samples[slot] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);  // final
+            for (int k = 0; k < ns; ++k) w.sq_w[(size_t)k * P + slot] = make_float4(0.f, 0.f, 0.f, -1.0f);
+            return;
+        }
+        V3 p1, e1, e2; int idx, quad;
+        load_tri<SMALL>(c, pos, p1, e1, e2, idx, quad);
+        Hit h; h.t = hr.x; h.u = hr.y; h.v = hr.z; h.pos = pos; h.idx = idx;
+        V3 p, nrm;
+        hit_point_normal(e1, e2, o, d, h, p, nrm);
+        nrm = dot(nrm, d) < 0.0f ? nrm : mul(nrm, -1.0f);
+        a.samples[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // pending (w = 0)
+        w.slot_p[slot] = make_float4(p.x, p.y, p.z, 0.0f);
+        for (int k = 0; k < ns; ++k) {
+            const V3 wi = sample_hemisphere_cosine(nrm, seed);
+            w.sq_w[(size_t)k * P + slot] = make_float4(wi.x, wi.y, wi.z, a.ao_max_dist);
+        }
+        return;
+    }
+    // DIRECT
+    {
+        w.sq_w[slot] = make_float4(0.f, 0.f, 0.f, -1.0f);
+        if (pos < 0) { a.samples[slot] = make_float4(0.45f, 0.45f, 0.45f, 1.0f); return; }
+        V3 p1, e1, e2; int idx, quad;
+        load_tri<SMALL>(c, pos, p1, e1, e2, idx, quad);
+        Hit h; h.t = hr.x; h.u = hr.y; h.v = hr.z; h.pos = pos; h.idx = idx;
+        V3 albedo, emissive; float roughness; int type;
+        load_mat<SMALL>(c, quad, albedo, roughness, emissive, type);
+        V3 p, nrm;
+        hit_point_normal(e1, e2, o, d, h, p, nrm);
+        const V3 col = mk(1.0f * emissive.x * 3.0f, 1.0f * emissive.y * 3.0f, 1.0f * emissive.z * 3.0f);
+        nrm = dot(nrm, d) < 0.0f ? nrm : mul(nrm, -1.0f);
+        const V3 wo = neg(d);
+        const float xi1 = random_float(seed);
+        const float xi2 = random_float(seed);
+        const V3 lp = mk(a.light_p1[0], a.light_p1[1], a.light_p1[2]);
+        const V3 ea = mk(a.light_ea[0], a.light_ea[1], a.light_ea[2]);
+        const V3 eb = mk(a.light_eb[0], a.light_eb[1], a.light_eb[2]);
+        const V3 Pl = add(add(lp, mul(ea, xi1)), mul(eb, xi2));
+        const V3 L = sub(Pl, p);
+        const float dist2 = dot(L, L);
+        const float dist = sqrtf(dist2);
+        const V3 wi = normalize(L);
+        const V3 lc = cross(ea, eb);
+        const float area = sqrtf(dot(lc, lc));
+        const V3 nl = normalize(lc);
+        const float cos_s = dot(wi, nrm);
+        const float cos_l = -dot(wi, nl);
+        if (cos_s > 0.0f && cos_l > 0.0f) {
+            const Ray s = get_ray(add(p, mul(wi, 0.01f)), wi);
+            V3 lalb, lem; float lr; int lt;
+            load_mat<SMALL>(c, a.light_quad, lalb, lr, lem, lt);
+            V3 f;
+            if (type == PTB_SPECULAR) {
+                const V3 wh = normalize(add(wo, wi));
+                const float D = distribution_ggx(dot(nrm, wh), roughness);
+                const float k = D / (4.0f * dot(wi, nrm) * dot(wo, nrm));
+                f = mk(k * albedo.x * 2.0f, k * albedo.y * 2.0f, k * albedo.z * 2.0f);
+            } else {
+                f = mul(albedo, PTD_INV_PI);
+            }
+            const float G = cos_s * cos_l / dist2;
+            w.sq_w[slot] = make_float4(s.o.x, s.o.y, s.o.z, dist - 0.02f);
+            w.sq_d[slot] = make_float4(s.d.x, s.d.y, s.d.z, 0.0f);
+            w.sq_c[slot] = make_float4(f.x * (lem.x * 3.0f) * G * area, f.y * (lem.y * 3.0f) * G * area,
+                                       f.z * (lem.z * 3.0f) * G * area, 0.0f);
+            w.slot_p[slot] = make_float4(col.x, col.y, col.z, 0.0f);
+        } else {
+            a.samples[slot] = make_float4(cl_max(col.x, 0.0f), cl_max(col.y, 0.0f), cl_max(col.z, 0.0f), 1.0f);
+        }
+    }
+}
+
+// ---- shadow / AO any-hit stage -----------------------------------------------------------------------
+template <int MODE, bool BVH, bool SMALL, bool STATS>
+__global__ void __launch_bounds__(128) wf_shadow(const SceneDev sc, const RenderArgs a, const WfBuffers w,
+                                                 const long long n_rays, unsigned long long* counters) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long P = (long long)a.frames_in_batch * a.n_local;
+    uint32_t nrays = 0;
+    QueryStats qs{0u, 0u};
+    if (i < n_rays) {
+        const float4 rw = w.sq_w[i];
+        int res = -2;
+        if (rw.w >= 0.0f || rw.w != rw.w) {  // holes carry tmax = -1
+            V3 o, d;
+            if (MODE == PTB_MODE_AO) {
+                const long long slot = i % P;
+                const V3 p = xyz(w.slot_p[slot]);
+                const V3 wi = xyz(rw);
+                const Ray s = get_ray(add(p, mul(wi, 0.01f)), wi);
+                o = s.o; d = s.d;
+            } else {
+                o = xyz(rw);
+                d = xyz(w.sq_d[i]);
+            }
+            Hit b;
+            const bool occ = q_any<BVH, SMALL, STATS>(c, o, d, rw.w, b, qs);
+            nrays = 1;
+            res = occ ? b.idx : -1;
+            if (MODE == PTB_MODE_DIRECT) {
+                V3 col = xyz(w.slot_p[i]);
+                if (!occ) {
+                    const V3 cc = xyz(w.sq_c[i]);
+                    col = mk(col.x + cc.x, col.y + cc.y, col.z + cc.z);
+                }
+                a.samples[i] = make_float4(cl_max(col.x, 0.0f), cl_max(col.y, 0.0f), cl_max(col.z, 0.0f), 1.0f);
+                if constexpr (STATS) {
+                    ptb_pixel_stats* s = w.slot_stats + i;
+                    s->visits_secondary += qs.visits;
+                    s->id_hash = s->id_hash * 31u + (uint32_t)(res + 2);
+                    s->tri_tests += qs.tests;
+                    if (!occ) s->count = 1;
+                }
+            }
+        }
+        if (MODE == PTB_MODE_AO) {
+            w.sq_res[i] = res;
+            if constexpr (STATS) { w.sq_visits[i] = qs.visits; w.sq_tests[i] = qs.tests; }
+        }
+    }
+    flush_counter(counters, CTR_ANY, nrays);
+    if (STATS) {
+        flush_counter(counters, CTR_NODES, qs.visits);
+        flush_counter(counters, CTR_TESTS, qs.tests);
+    }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(256) wf_finish_ao(const RenderArgs a, const WfBuffers w) {
+    const long long P = (long long)a.frames_in_batch * a.n_local;
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= P) return;
+    if (a.samples[slot].w != 0.0f) return;  // primary miss: already final
+    const int ns = a.ao_samples;
+    uint32_t open = 0;
+    for (int k = 0; k < ns; ++k) {
+        const int res = w.sq_res[(size_t)k * P + slot];
+        if (res == -1) open++;
+        if constexpr (STATS) {
+            ptb_pixel_stats* s = w.slot_stats + slot;
+            s->visits_secondary += w.sq_visits[(size_t)k * P + slot];
+            s->tri_tests += w.sq_tests[(size_t)k * P + slot];
+            s->id_hash = s->id_hash * 31u + (uint32_t)(res + 2);
+        }
+    }
+    if constexpr (STATS) w.slot_stats[slot].count = open;
+    const float v = (float)open / (float)ns;
+    a.samples[slot] = make_float4(v, v, v, 1.0f);
+}
+
+// copy the statistics of the slots that belong to stats_frame
+__global__ void __launch_bounds__(256) wf_export_stats(const RenderArgs a, const WfBuffers w) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= a.n_local) return;
+    const int fi = a.stats_frame - a.first_frame;
+    if (fi < 0 || fi >= a.frames_in_batch) return;
+    const uint4* s = reinterpret_cast<const uint4*>(w.slot_stats + (size_t)fi * a.n_local + li);
+    uint4* d = reinterpret_cast<uint4*>(a.stats + li);
+    d[0] = s[0];
+    d[1] = s[1];
+}
+
+// ---- host orchestration ------------------------------------------------------------------------------
+
+#define WF_TRY(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) return ptb::fail(PTB_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+template <class K>
+static int wf_smem(K kernel, size_t smem) {
+    if (smem > 48 * 1024) WF_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
+}
+
+template <bool BVH, bool SMALL, bool STATS>
+static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArgs& a, const WfBuffers& w,
+                  unsigned long long* counters) {
+    const long long P = (long long)a.frames_in_batch * a.n_local;
+    const int block = 128;
+    const unsigned grid = (unsigned)((P + block - 1) / block);
+    const size_t smem_q = scene_smem_bytes(sc, BVH, SMALL, block);
+    const size_t smem_s = scene_smem_bytes(sc, false, SMALL, block);
+    int rc;
+    wf_generate<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(a, w, STATS ? 1 : 0);
+    WF_TRY(cudaGetLastError());
+    auto ext = wf_extend<BVH, SMALL, STATS>;
+    if ((rc = wf_smem(ext, smem_q))) return rc;
+    if (mode == PTB_MODE_PATH) {
+        auto shade = wf_shade_path<BVH, SMALL, STATS>;
+        if ((rc = wf_smem(shade, smem_s))) return rc;
+        for (int depth = 0; depth < a.max_depth; ++depth) {
+            const int qi = depth & 1;
+            ext<<<grid, block, smem_q, st>>>(sc, w, depth, qi, counters);
+            shade<<<grid, block, smem_s, st>>>(sc, a, w, depth, qi);
+        }
+        WF_TRY(cudaGetLastError());
+    } else {
+        ext<<<grid, block, smem_q, st>>>(sc, w, 0, 0, counters);
+        WF_TRY(cudaGetLastError());
+        if (mode == PTB_MODE_PRIMARY) {
+            auto k = wf_shade_first<PTB_MODE_PRIMARY, BVH, SMALL, STATS>;
+            if ((rc = wf_smem(k, smem_s))) return rc;
+            k<<<grid, block, smem_s, st>>>(sc, a, w);
+        } else if (mode == PTB_MODE_AO) {
+            auto k = wf_shade_first<PTB_MODE_AO, BVH, SMALL, STATS>;
+            if ((rc = wf_smem(k, smem_s))) return rc;
+            k<<<grid, block, smem_s, st>>>(sc, a, w);
+            const long long nr = P * a.ao_samples;
+            auto sh = wf_shadow<PTB_MODE_AO, BVH, SMALL, STATS>;
+            if ((rc = wf_smem(sh, smem_q))) return rc;
+            sh<<<(unsigned)((nr + block - 1) / block), block, smem_q, st>>>(sc, a, w, nr, counters);
+            wf_finish_ao<STATS><<<(unsigned)((P + 255) / 256), 256, 0, st>>>(a, w);
+        } else {
+            auto k = wf_shade_first<PTB_MODE_DIRECT, BVH, SMALL, STATS>;
+            if ((rc = wf_smem(k, smem_s))) return rc;
+            k<<<grid, block, smem_s, st>>>(sc, a, w);
+            auto sh = wf_shadow<PTB_MODE_DIRECT, BVH, SMALL, STATS>;
+            if ((rc = wf_smem(sh, smem_q))) return rc;
+            sh<<<grid, block, smem_q, st>>>(sc, a, w, P, counters);
+        }
+        WF_TRY(cudaGetLastError());
+    }
+    if (STATS && a.stats) {
+        wf_export_stats<<<(a.n_local + 255) / 256, 256, 0, st>>>(a, w);
+        WF_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+// scratch layout for one batch; (re)allocates *scratch when it is too small
+static int wavefront_render(cudaStream_t st, void** scratch, size_t* scratch_bytes, unsigned long long* counters,
+                            int mode, const SceneDev& sc, const RenderArgs& a, bool bvh, bool small, bool stats,
+                            int /*sm_count*/) {
+    const size_t P = (size_t)a.frames_in_batch * a.n_local;
+    const size_t n_shadow = mode == PTB_MODE_AO ? P * (size_t)a.ao_samples : (mode == PTB_MODE_DIRECT ? P : 0);
+    const size_t n_counts = (size_t)a.max_depth + 2;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const bool path = mode == PTB_MODE_PATH;
+    const size_t o_qo0 = take(P * 16), o_qd0 = take(P * 16), o_qm0 = take(P * 16);
+    const size_t o_qo1 = take(path ? P * 16 : 0), o_qd1 = take(path ? P * 16 : 0), o_qm1 = take(path ? P * 16 : 0);
+    const size_t o_hit = take(P * 16);
+    const size_t o_rad = take(path ? P * 16 : 0);
+    const size_t o_slotp = take(!path ? P * 16 : 0);
+    const size_t o_sqw = take(n_shadow * 16);
+    const size_t o_sqd = take(mode == PTB_MODE_DIRECT ? P * 16 : 0);
+    const size_t o_sqc = take(mode == PTB_MODE_DIRECT ? P * 16 : 0);
+    const size_t o_res = take(mode == PTB_MODE_AO ? n_shadow * 4 : 0);
+    const size_t o_vis = take(mode == PTB_MODE_AO && stats ? n_shadow * 4 : 0);
+    const size_t o_tst = take(mode == PTB_MODE_AO && stats ? n_shadow * 4 : 0);
+    const size_t o_stats = take(stats ? P * sizeof(ptb_pixel_stats) : 0);
+    const size_t o_counts = take(n_counts * 4);
+    if (*scratch_bytes < off) {
+        if (*scratch) WF_TRY(cudaFree(*scratch));
+        *scratch = nullptr; *scratch_bytes = 0;
+        WF_TRY(cudaMalloc(scratch, off));
+        *scratch_bytes = off;
+    }
+    char* base = static_cast<char*>(*scratch);
+    WfBuffers w;
+    w.q_o[0] = (float4*)(base + o_qo0); w.q_d[0] = (float4*)(base + o_qd0); w.q_m[0] = (float4*)(base + o_qm0);
+    w.q_o[1] = (float4*)(base + o_qo1); w.q_d[1] = (float4*)(base + o_qd1); w.q_m[1] = (float4*)(base + o_qm1);
+    w.hit = (float4*)(base + o_hit);
+    w.radiance = (float4*)(base + o_rad);
+    w.slot_p = (float4*)(base + o_slotp);
+    w.sq_w = (float4*)(base + o_sqw); w.sq_d = (float4*)(base + o_sqd); w.sq_c = (float4*)(base + o_sqc);
+    w.sq_res = (int*)(base + o_res); w.sq_visits = (uint32_t*)(base + o_vis); w.sq_tests = (uint32_t*)(base + o_tst);
+    w.slot_stats = (ptb_pixel_stats*)(base + o_stats);
+    w.counts = (unsigned int*)(base + o_counts);
+    WF_TRY(cudaMemsetAsync(w.counts, 0, n_counts * 4, st));
+#define WF_CASE(B, S, T) if (bvh == B && small == S && stats == T) return wf_run<B, S, T>(st, mode, sc, a, w, counters)
+    WF_CASE(true, true, false); WF_CASE(true, true, true); WF_CASE(true, false, false); WF_CASE(true, false, true);
+    WF_CASE(false, true, false); WF_CASE(false, true, true); WF_CASE(false, false, false); WF_CASE(false, false, true);
+#undef WF_CASE
+    return ptb::fail(PTB_E_INVALID, "wavefront_render: unreachable");
+}
+
+}  // namespace ptd

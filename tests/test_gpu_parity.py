@@ -1,0 +1,370 @@
+"""GPU parity tests: the sm_100a path, called through the C-ABI, against the CPU oracle.
+
+Bit-exact bar: hit triangle ids, t/u/v bits, BVH node-visit counts, ray counts and radiance bits all
+equal the oracle's.  The north-star tolerance for radiance (relative RMSE <= 1e-3 at equal spp and RNG
+stream) is asserted too -- it is implied by bit equality, and is the bar if a libm-free kernel ever
+has to change.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, SCENE, bits, oracle_params
+
+pytestmark = pytest.mark.gpu
+
+RRMSE_TOL = 1e-3  # north_star: relative RMSE <= 1e-3 at equal spp with an identical RNG stream
+
+
+def rrmse(a, b):
+    a = a[:, :3].astype(np.float64)
+    b = b[:, :3].astype(np.float64)
+    return float(np.sqrt(np.mean((a - b) ** 2)) / max(np.sqrt(np.mean(b ** 2)), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def scene(dev, cornell):
+    tris, mats = cornell
+    s = dev.scene(tris, mats)
+    yield s
+    s.close()
+
+
+# ---- numerics contract ---------------------------------------------------------------------------
+
+def test_device_is_blackwell(dev):
+    assert "sm_10" in dev.name() and dev.sm_count() >= 100
+
+
+def test_sincos_bit_exact(dev, ob):
+    x = np.concatenate([np.linspace(0, 2 * np.pi, 2_000_001), np.random.default_rng(0).uniform(0, 6.2831855, 500_000),
+                        [0.0, 6.2831855, 1.5707964, 3.1415927, 4.712389]]).astype(np.float32)
+    s, c = dev.test_sincos(x)
+    so, co = ob.sincos(x)
+    np.testing.assert_array_equal(bits(s), bits(so))
+    np.testing.assert_array_equal(bits(c), bits(co))
+
+
+def test_pow_bit_exact(dev, ob):
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(0, 1, 400_000), rng.uniform(0, 300, 400_000), 10.0 ** rng.uniform(-44, 38, 100_000),
+                        [0.0, 1.0, np.inf, np.nan, -1.0, 1e-45, 3.4e38]]).astype(np.float32)
+    for y in (np.float32(2.2), np.float32(1.0) / np.float32(2.2)):
+        np.testing.assert_array_equal(bits(dev.test_pow(x, y)), bits(ob.powf(x, y)))
+
+
+def test_rng_known_answers_on_device(dev):
+    kat = json.load(open(os.path.join(GOLDEN, "rng_kat.json")))
+    for case in kat["cases"]:
+        st, va = dev.test_rng(case["gid"], case["frame"], len(case["states"]))
+        assert st.tolist() == case["states"]
+        assert bits(va).tolist() == case["value_bits"]
+
+
+@pytest.mark.parametrize("w,h,frame", [(512, 512, 0), (1920, 1080, 7), (100, 37, 3)])
+def test_camera_bit_exact(dev, ob, w, h, frame):
+    rng = np.random.default_rng(w)
+    gids = np.unique(np.concatenate([rng.integers(0, w * h, 2000), [0, w - 1, w * h - 1]])).astype(np.int32)
+    o, d, s = dev.test_camera(w, h, frame, gids)
+    for k, gid in enumerate(gids):
+        seed = (int(gid) + ob.lib().ora_hash_uint32(frame)) & 0xFFFFFFFF
+        oo, od, os_ = ob.generate_ray(int(gid) % w, int(gid) // w, w, h, seed)
+        assert bits(o[k]).tolist() == bits(oo).tolist() and bits(d[k]).tolist() == bits(od).tolist() and s[k] == os_
+
+
+# ---- scene queries ------------------------------------------------------------------------------------
+
+def _rays(n, seed):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform([-2.7, 0.05, -5.5], [2.7, 5.4, 3.9], (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d[:64] = np.float32([0, 0, -1])
+    d[64:128] = np.float32([0, -1, 0])
+    d[128:192] = np.float32([-1, 0, 0])
+    d[192:200] = np.float32([np.nan, 0, 1])  # NaN rays must terminate identically
+    return o, d
+
+
+@pytest.mark.parametrize("any_hit", [False, True])
+def test_trace_hit_ids_and_visit_counts(dev, pt, ob, cornell, cornell_bvh, scene, any_hit):
+    tris, _ = cornell
+    _, bvh, _ = cornell_bvh
+    o, d = _rays(300_000, 11)
+    tmax = np.float32(2.5) if any_hit else np.float32(1e20)
+    g_bvh = dev.trace(scene, o, d, tmax, accel=pt.ACCEL_BVH, any_hit=any_hit)
+    g_bru = dev.trace(scene, o, d, tmax, accel=pt.ACCEL_BRUTE, any_hit=any_hit)
+    o_bvh = ob.trace(tris, o, d, tmax, bvh=bvh, any_hit=any_hit)
+    o_bru = ob.trace(tris, o, d, tmax, bvh=None, any_hit=any_hit)
+    for f in ("tri", "t", "u", "v", "visits", "tests"):  # same traversal, same counts
+        np.testing.assert_array_equal(bits(g_bvh[f]), bits(o_bvh[f]), err_msg=f"bvh {f}")
+        np.testing.assert_array_equal(bits(g_bru[f]), bits(o_bru[f]), err_msg=f"brute {f}")
+    if not any_hit:  # closest hit is order independent: BVH == the reference's brute-force loop
+        for f in ("tri", "t", "u", "v"):
+            np.testing.assert_array_equal(bits(g_bvh[f]), bits(o_bru[f]))
+    else:
+        np.testing.assert_array_equal(g_bvh["tri"] >= 0, o_bru["tri"] >= 0)
+    assert (g_bvh["tests"] <= 36).all() and g_bvh["visits"].max() <= 17
+
+
+# ---- the hot path: every mode x integrator x accel ----------------------------------------------------
+
+MODES = {"primary": 0, "ao": 1, "direct": 2, "path": 3}
+
+
+@pytest.mark.parametrize("integrator", ["mega", "wavefront"])
+@pytest.mark.parametrize("accel", ["bvh", "brute"])
+@pytest.mark.parametrize("mode", list(MODES))
+def test_render_bit_exact(dev, pt, ob, cornell, cornell_bvh, scene, mode, accel, integrator):
+    tris, mats = cornell
+    _, bvh, _ = cornell_bvh
+    w, h, nf = 96, 80, 3
+    use_bvh = accel == "bvh"
+    prm = pt.default_params(width=w, height=h, n_frames=nf, mode=MODES[mode], accum=pt.ACCUM_LINEAR, max_depth=8,
+                            accel=pt.ACCEL_BVH if use_bvh else pt.ACCEL_BRUTE, collect_stats=1, frames_per_batch=2,
+                            integrator=pt.INTEGRATOR_MEGAKERNEL if integrator == "mega" else pt.INTEGRATOR_WAVEFRONT)
+    frame = dev.buffer(w * h * 16)
+    stats = dev.buffer(w * h * 32)
+    ctr = dev.render(scene, prm, frame, stats, want_counters=True)
+    fb = frame.read(np.float32).reshape(-1, 4)
+    st = stats.read(pt.STATS_DTYPE)
+    frame.close(); stats.close()
+    oprm = oracle_params(ob, tris, w, h, n_frames=nf, mode=MODES[mode], accum=ob.ACCUM_LINEAR, max_depth=8,
+                         use_bvh=1 if use_bvh else 0)
+    ofb, ost, octr = ob.render(oprm, tris, mats, bvh=bvh if use_bvh else None, want_stats=True)
+    for f in ost.dtype.names:
+        np.testing.assert_array_equal(st[f], ost[f], err_msg=f)
+    np.testing.assert_array_equal(bits(fb), bits(ofb))
+    assert rrmse(fb, ofb) <= RRMSE_TOL
+    for k in ("rays_closest", "rays_any", "nodes", "tri_tests", "samples"):
+        assert ctr[k] == octr[k], k
+
+
+def test_golden_vectors_on_device(dev, pt, cornell, scene):
+    g = np.load(os.path.join(GOLDEN, "oracle_small.npz"))
+    nodes, order = scene.bvh()
+    assert nodes.view(np.uint8).tobytes() == g["bvh_nodes"].tobytes() and order.tolist() == g["bvh_order"].tolist()
+    tris, mats = cornell
+    for name, mode in MODES.items():
+        prm = pt.default_params(width=32, height=32, n_frames=3, mode=mode, accum=pt.ACCUM_LINEAR, max_depth=8, collect_stats=1)
+        fb, st, ctr = dev.render_host(tris, mats, prm, want_stats=True)
+        assert fb.tobytes() == g[f"{name}_fb"].tobytes(), name
+        assert st.tobytes() == g[f"{name}_stats"].tobytes(), name
+        assert [ctr[k] for k in ("rays_closest", "rays_any", "nodes", "tri_tests")] == g[f"{name}_ctr"].tolist()
+
+
+# ---- the reference's own flow: GenerateColors launched frame by frame ---------------------------------
+
+def test_launch1d_drop_in_flow(dev, pt, ob, cornell):
+    """RaytraceTest.cpp:216-268: upload tBuffer/materialBuffer, launch GenerateColors per frame with
+    int4{W,H,frame,-}, read the gamma-space framebuffer back."""
+    tris, mats = cornell
+    w = h = 64
+    nf = 6
+    tb = dev.buffer(36 * 64 * 64)   # the reference over-allocates: nElems is passed a byte count (:222)
+    mb = dev.buffer(18 * 64 * 64)
+    fbuf = dev.buffer(w * h * 16)
+    tb.write(tris); mb.write(mats)
+    k = dev.kernel("../test/ClKernels/GenerateColors", "GenerateColors")
+    for frame in range(nf):
+        dev.launch1d(k, [tb, mb, fbuf], pt.Int4(w, h, frame, 0), w * h)
+    dev.sync()
+    got = fbuf.read(np.float32).reshape(-1, 4)
+    want, _, _ = ob.render(ob.default_params(w, h, first_frame=0, n_frames=nf, mode=3, accum=ob.ACCUM_REFERENCE, use_bvh=0), tris, mats)
+    np.testing.assert_array_equal(bits(got), bits(want))
+    assert (pt.to_rgb8(got) == ob.to_rgb8(want)).all()
+    # brute-force variant of the same kernel (ACCEL option) gives the same bits
+    dev.kernel_set_int(k, "ACCEL", pt.ACCEL_BRUTE)
+    fbuf.clear()
+    for frame in range(nf):
+        dev.launch1d(k, [tb, mb, fbuf], pt.Int4(w, h, frame, 0), w * h)
+    dev.sync()
+    np.testing.assert_array_equal(bits(fbuf.read(np.float32).reshape(-1, 4)), bits(want))
+    dev.kernel_set_int(k, "ACCEL", pt.ACCEL_BVH)
+    # changing the scene buffer is picked up (scene cache keyed on buffer version)
+    t2 = tris.copy(); t2["p1"][10:12, 1] -= 1.0; t2["p2"][10:12, 1] -= 1.0; t2["p3"][10:12, 1] -= 1.0
+    tb.write(t2); fbuf.clear()
+    dev.launch1d(k, [tb, mb, fbuf], pt.Int4(w, h, 0, 0), w * h)
+    dev.sync()
+    want2, _, _ = ob.render(ob.default_params(w, h, n_frames=1, mode=3, accum=ob.ACCUM_REFERENCE), t2, mats)
+    np.testing.assert_array_equal(bits(fbuf.read(np.float32).reshape(-1, 4)), bits(want2))
+    with pytest.raises(pt.PtbError, match="n_threads"):
+        dev.launch1d(k, [tb, mb, fbuf], pt.Int4(w, h, 0, 0), w * h + 64)
+    with pytest.raises(pt.PtbError, match="no kernel"):
+        dev.kernel("../test/ClKernels/TestKernel", "VectorAdd")
+    for b in (tb, mb, fbuf):
+        b.close()
+
+
+def test_reference_accum_batched_equals_per_frame(dev, pt, ob, cornell, scene):
+    tris, mats = cornell
+    w, h = 48, 48
+    want, _, _ = ob.render(ob.default_params(w, h, first_frame=0, n_frames=7, mode=3, accum=ob.ACCUM_REFERENCE), tris, mats)
+    for integ in (pt.INTEGRATOR_MEGAKERNEL, pt.INTEGRATOR_WAVEFRONT):
+        frame = dev.buffer(w * h * 16)
+        dev.render(scene, pt.default_params(width=w, height=h, first_frame=0, n_frames=3, frames_per_batch=2, integrator=integ), frame)
+        dev.render(scene, pt.default_params(width=w, height=h, first_frame=3, n_frames=4, frames_per_batch=3, integrator=integ), frame)
+        np.testing.assert_array_equal(bits(frame.read(np.float32).reshape(-1, 4)), bits(want))
+        frame.close()
+
+
+# ---- sharding, ragged sizes, degenerate scenes ----------------------------------------------------------
+
+def test_sharded_render_is_bit_identical(dev, pt, ob, cornell, scene):
+    from oclpathtracer_b200 import sharding
+    import torch
+
+    tris, mats = cornell
+    w, h, world, block = 100, 37, 4, 64  # 3700 pixels: ragged
+    full, _, _ = ob.render(ob.default_params(w, h, n_frames=2, mode=3, accum=1, max_depth=6), tris, mats)
+    parts = []
+    for r in range(world):
+        prm = pt.default_params(width=w, height=h, n_frames=2, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR, max_depth=6,
+                                shard_index=r, shard_count=world, shard_block=block)
+        fb, _, _ = dev.render_host(tris, mats, prm)
+        assert len(fb) == sharding.local_pixels(w * h, r, world, block)
+        parts.append(torch.from_numpy(fb))
+    img = sharding.assemble(parts, w * h, world, block).numpy()
+    np.testing.assert_array_equal(bits(img), bits(full))
+
+
+def test_single_triangle_and_miss_paths(dev, pt, ob, cornell):
+    tris, mats = cornell
+    one = tris[10:11].copy()  # half of the light, seen from below
+    for mode in (0, 1, 2, 3):
+        prm = pt.default_params(width=64, height=64, n_frames=2, mode=mode, accum=pt.ACCUM_LINEAR, max_depth=4, collect_stats=1)
+        for integ in (pt.INTEGRATOR_MEGAKERNEL, pt.INTEGRATOR_WAVEFRONT):
+            prm.integrator = integ
+            fb, st, ctr = dev.render_host(one, mats, prm, want_stats=True)
+            b = pt.build_bvh_host(one)
+            bvh, _keep = ob.make_bvh(b["nodes"], b["tri_order"])
+            oprm = oracle_params(ob, tris, 64, 64, n_frames=2, mode=mode, accum=1, max_depth=4, use_bvh=1)
+            ofb, ost, octr = ob.render(oprm, one, mats, bvh=bvh, want_stats=True)
+            np.testing.assert_array_equal(bits(fb), bits(ofb))
+            assert st.tobytes() == ost.tobytes()
+            assert (st["tri"] == -1).any() and (st["tri"] == 0).any()
+
+
+def test_tessellated_scene_global_memory_path(dev, pt, ob, cornell):
+    """k=12 -> 5184 triangles: nodes beyond the shared-memory prefix and triangles come from global memory."""
+    tris, mats = cornell
+    big = pt.tessellate(tris, 12)
+    p1, ea, eb = pt.light_from_quad(tris, 5)
+    bp = pt.bvh_params(smem_nodes=128)
+    sc = dev.scene(big, mats, bp)
+    info = sc.info()
+    assert info["n_nodes"] > info["smem_nodes"] == 128
+    nodes, order = sc.bvh()
+    bvh, _keep = ob.make_bvh(nodes, order)
+    w, h = 64, 64
+    for mode in (0, 1, 2, 3):
+        for integ in (pt.INTEGRATOR_MEGAKERNEL, pt.INTEGRATOR_WAVEFRONT):
+            prm = pt.default_params(width=w, height=h, n_frames=2, mode=mode, accum=pt.ACCUM_LINEAR, max_depth=6,
+                                    collect_stats=1, integrator=integ, light_p1=p1, light_ea=ea, light_eb=eb)
+            frame, stats = dev.buffer(w * h * 16), dev.buffer(w * h * 32)
+            ctr = dev.render(sc, prm, frame, stats, want_counters=True)
+            fb, st = frame.read(np.float32).reshape(-1, 4), stats.read(pt.STATS_DTYPE)
+            frame.close(); stats.close()
+            oprm = ob.default_params(w, h, n_frames=2, mode=mode, accum=1, max_depth=6, use_bvh=1, light_p1=p1, light_ea=ea, light_eb=eb)
+            ofb, ost, octr = ob.render(oprm, big, mats, bvh=bvh, want_stats=True)
+            np.testing.assert_array_equal(bits(fb), bits(ofb), err_msg=f"mode {mode} integ {integ}")
+            assert st.tobytes() == ost.tobytes()
+            assert ctr["nodes"] == octr["nodes"] and ctr["tri_tests"] == octr["tri_tests"]
+    # sampled ground truth: BVH hits == the reference's brute-force loop over all 5184 triangles
+    o, d = _rays(20_000, 5)
+    g = dev.trace(sc, o, d, np.float32(1e20), accel=pt.ACCEL_BVH)
+    r = ob.trace(big, o, d, np.float32(1e20), bvh=None)
+    for f in ("tri", "t", "u", "v"):
+        np.testing.assert_array_equal(bits(g[f]), bits(r[f]))
+    sc.close()
+
+
+# ---- BASELINE.json configurations at full size: size-independent properties -----------------------------
+
+def _render(dev, pt, scene, **kw):
+    prm = pt.default_params(**kw)
+    n = pt.local_pixels(prm)
+    frame = dev.buffer(n * 16)
+    ctr = dev.render(scene, prm, frame, None, want_counters=True)
+    fb = frame.read(np.float32).reshape(-1, 4)
+    frame.close()
+    return fb, ctr
+
+
+def test_c1_primary_512_full_size_vs_oracle(dev, pt, ob, cornell, cornell_bvh, scene):
+    """configs[0]: 512x512 primary rays, 1 spp, hit-ID output -- small enough to check every pixel."""
+    tris, mats = cornell
+    _, bvh, _ = cornell_bvh
+    prm = pt.default_params(width=512, height=512, n_frames=1, mode=pt.MODE_PRIMARY, accum=pt.ACCUM_LINEAR, collect_stats=1)
+    fb, st, ctr = dev.render_host(tris, mats, prm, want_stats=True)
+    ofb, ost, octr = ob.render(ob.default_params(512, 512, mode=0, accum=1, use_bvh=1), tris, mats, bvh=bvh, want_stats=True)
+    brute, bst, _ = ob.render(ob.default_params(512, 512, mode=0, accum=1, use_bvh=0), tris, mats, want_stats=True)
+    assert st.tobytes() == ost.tobytes() and fb.tobytes() == ofb.tobytes()
+    np.testing.assert_array_equal(st["tri"], bst["tri"])  # == the reference's brute-force hit ids
+    np.testing.assert_array_equal(st["t_bits"], bst["t_bits"])
+    assert ctr["rays_closest"] == 512 * 512
+
+
+def test_c2_ao_1024_full_size_properties(dev, pt, scene):
+    """configs[1]: AO 1024x1024, 16 rays/pixel.  BVH == brute force == wavefront, bit for bit; values are k/16."""
+    kw = dict(width=1024, height=1024, n_frames=1, mode=pt.MODE_AO, accum=pt.ACCUM_LINEAR, ao_samples=16)
+    a, ca = _render(dev, pt, scene, accel=pt.ACCEL_BVH, integrator=pt.INTEGRATOR_MEGAKERNEL, **kw)
+    b, cb = _render(dev, pt, scene, accel=pt.ACCEL_BRUTE, integrator=pt.INTEGRATOR_MEGAKERNEL, **kw)
+    c, cc = _render(dev, pt, scene, accel=pt.ACCEL_BVH, integrator=pt.INTEGRATOR_WAVEFRONT, **kw)
+    assert a.tobytes() == b.tobytes() == c.tobytes()
+    assert ca["rays_closest"] == 1024 * 1024 and ca["rays_any"] == 16 * 1024 * 1024 == cc["rays_any"] == cb["rays_any"]
+    v = a[:, 0] * 16
+    assert np.array_equal(v, np.round(v)) and v.min() >= 0 and v.max() <= 16
+    assert np.array_equal(a[:, 0], a[:, 1]) and np.array_equal(a[:, 3], np.ones(len(a), np.float32))
+
+
+def test_c3_direct_1080p_properties(dev, pt, scene):
+    """configs[2] geometry at 4 of its 64 spp: integrators and accelerators agree bit for bit."""
+    kw = dict(width=1920, height=1080, n_frames=4, mode=pt.MODE_DIRECT, accum=pt.ACCUM_LINEAR)
+    a, ca = _render(dev, pt, scene, accel=pt.ACCEL_BVH, integrator=pt.INTEGRATOR_MEGAKERNEL, **kw)
+    b, cb = _render(dev, pt, scene, accel=pt.ACCEL_BRUTE, integrator=pt.INTEGRATOR_WAVEFRONT, **kw)
+    assert a.tobytes() == b.tobytes() and ca["rays_any"] == cb["rays_any"] > 0
+    assert np.isfinite(a).all() and a[:, :3].min() >= 0
+
+
+def test_c4_path_4k_properties(dev, pt, scene):
+    """configs[3] geometry (4K, max depth 8) at 2 of its 256 spp: megakernel == wavefront; linearity of the
+    frame mean: mean(f0,f1) == (mean(f0) + mean(f1)) / 2 computed from single-frame renders."""
+    kw = dict(width=3840, height=2160, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR, max_depth=8)
+    a, ca = _render(dev, pt, scene, n_frames=2, integrator=pt.INTEGRATOR_MEGAKERNEL, **kw)
+    b, cb = _render(dev, pt, scene, n_frames=2, integrator=pt.INTEGRATOR_WAVEFRONT, **kw)
+    assert a.tobytes() == b.tobytes() and ca["rays_closest"] == cb["rays_closest"]
+    f0, _ = _render(dev, pt, scene, first_frame=0, n_frames=1, **kw)
+    f1, _ = _render(dev, pt, scene, first_frame=1, n_frames=1, **kw)
+    want = (f0[:, :3] + f1[:, :3]) / np.float32(2.0)
+    np.testing.assert_array_equal(bits(a[:, :3]), bits(want))
+    assert ca["rays_closest"] <= 8 * 2 * 3840 * 2160
+
+
+def test_buffer_map_unmap_and_errors(dev, pt):
+    import ctypes as C
+    b = dev.buffer(1024)
+    hp = C.c_void_p()
+    assert pt.lib().ptb_buffer_map(b._h, C.byref(hp)) == 0
+    dev.sync()
+    arr = (C.c_uint8 * 1024).from_address(hp.value)
+    for i in range(1024):
+        arr[i] = i & 255
+    assert pt.lib().ptb_buffer_unmap(b._h, hp) == 0
+    dev.sync()
+    assert b.read(np.uint8).tolist() == [i & 255 for i in range(1024)]
+    assert pt.lib().ptb_buffer_unmap(b._h, C.c_void_p(1234)) != 0
+    with pytest.raises(pt.PtbError, match="range exceeds"):
+        b.write(np.zeros(2048, np.uint8))
+    b.close()
+    tiny = dev.buffer(16)
+    with pytest.raises(pt.PtbError, match="too small"):
+        sc_tris, sc_mats = pt.load_model(SCENE)
+        s = dev.scene(sc_tris, sc_mats)
+        try:
+            dev.render(s, pt.default_params(width=8, height=8), tiny)
+        finally:
+            s.close()
+    tiny.close()

@@ -1,0 +1,182 @@
+"""CPU tests of the product's host side: C-ABI surface, loader, BVH builder, sharding, error paths."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SCENE
+
+
+def test_library_exports_every_declared_symbol(pt):
+    hdr = open(os.path.join(ROOT, "include", "ptb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(ptb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 40
+    lib = pt.lib()
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(pt.EXPORTS) == declared
+    assert lib.ptb_version() == 100
+
+
+def test_struct_sizes_match_reference_layout(pt):
+    # RaytraceTest.cpp:50-76 / GenerateColors.cl:12-28: 64-byte packed records
+    assert pt.TRIANGLE_DTYPE.itemsize == 64 and pt.MATERIAL_DTYPE.itemsize == 64
+    assert pt.TRIANGLE_DTYPE.fields["id"][1] == 48
+    assert pt.MATERIAL_DTYPE.fields["roughness"][1] == 32 and pt.MATERIAL_DTYPE.fields["type"][1] == 36
+    assert pt.NODE_DTYPE.itemsize == 64 and pt.BVH_TRI_DTYPE.itemsize == 48 and pt.STATS_DTYPE.itemsize == 32
+    assert C.sizeof(pt.RenderParams) % 4 == 0 and C.sizeof(pt.Counters) == 64
+
+
+def test_loader_matches_oracle_bytes(pt, ob):
+    t1, m1 = pt.load_model(SCENE)
+    t2, m2 = ob.load_model(SCENE)
+    assert t1.tobytes() == t2.tobytes() and m1.tobytes() == m2.tobytes()
+
+
+def test_loader_errors(pt, tmp_path):
+    with pytest.raises(pt.PtbError, match="cannot open"):
+        pt.load_model(str(tmp_path / "missing.bin"))
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(open(SCENE, "rb").read()[:700])
+    with pytest.raises(pt.PtbError, match="truncated"):
+        pt.load_model(str(bad))
+    empty = tmp_path / "empty.bin"
+    empty.write_bytes(b"")
+    with pytest.raises(pt.PtbError):
+        pt.load_model(str(empty))
+
+
+def _validate_bvh(pt, tris, b, pad_min=0.0):
+    nodes, order, otris = b["nodes"], b["tri_order"], b["ordered_tris"]
+    n = len(tris)
+    assert sorted(order.tolist()) == list(range(n))  # every triangle in exactly one leaf slot
+    np.testing.assert_array_equal(otris["index"], order)
+    np.testing.assert_array_equal(otris["quad"], tris["id"][order])
+    np.testing.assert_array_equal(otris["p1"], tris["p1"][order][:, :3])
+    np.testing.assert_array_equal(otris["e1"], (tris["p2"][order] - tris["p1"][order])[:, :3])  # GenerateColors.cl:92
+    np.testing.assert_array_equal(otris["e2"], (tris["p3"][order] - tris["p1"][order])[:, :3])  # GenerateColors.cl:93
+    tri_lo = np.minimum(np.minimum(tris["p1"], tris["p2"]), tris["p3"])[:, :3]
+    tri_hi = np.maximum(np.maximum(tris["p1"], tris["p2"]), tris["p3"])[:, :3]
+    covered = np.zeros(n, bool)
+    seen_nodes = np.zeros(len(nodes), bool)
+
+    def bounds(ref):
+        """returns (lo, hi) of the subtree; checks containment recursively (iteratively for depth safety)"""
+        if ref < 0:
+            code = (~ref) & 0xFFFFFFFF
+            first, count = code >> 3, (code & 7) + 1
+            assert 1 <= count <= 8 and first + count <= n
+            assert not covered[first:first + count].any()
+            covered[first:first + count] = True
+            idx = order[first:first + count]
+            assert (np.diff(idx) > 0).all() if count > 1 else True  # ascending caller index inside a leaf
+            return tri_lo[idx].min(0), tri_hi[idx].max(0)
+        assert not seen_nodes[ref]
+        seen_nodes[ref] = True
+        nd = nodes[ref]
+        l0, h0 = bounds(int(nd["child0"]))
+        l1, h1 = bounds(int(nd["child1"]))
+        assert (nd["lo0"] <= l0 - pad_min).all() and (nd["hi0"] >= h0 + pad_min).all()
+        assert (nd["lo1"] <= l1 - pad_min).all() and (nd["hi1"] >= h1 + pad_min).all()
+        return np.minimum(l0, l1), np.maximum(h0, h1)
+
+    import sys
+    sys.setrecursionlimit(10000)
+    bounds(0)
+    assert covered.all() and seen_nodes.all()
+
+
+def test_bvh_structure_cornell(pt, cornell):
+    tris, _ = cornell
+    b = pt.build_bvh_host(tris)
+    assert b["smem_nodes"] == len(b["nodes"]) <= 35 and 1 <= b["depth"] <= 12
+    _validate_bvh(pt, tris, b, pad_min=5e-4)  # default pad = 1e-4 * diagonal(9.6) ~ 9.6e-4
+
+
+@pytest.mark.parametrize("k,max_leaf", [(4, 4), (12, 2), (9, 8)])
+def test_bvh_structure_tessellated(pt, cornell, k, max_leaf):
+    tris, _ = cornell
+    big = pt.tessellate(tris, k)
+    b = pt.build_bvh_host(big, pt.bvh_params(max_leaf=max_leaf, smem_nodes=64))
+    assert b["smem_nodes"] == min(64, len(b["nodes"]))
+    _validate_bvh(pt, big, b, pad_min=5e-4)
+    # breadth-first prefix: children of early nodes come later, prefix is closed under "parent of"
+    kids = np.concatenate([b["nodes"]["child0"], b["nodes"]["child1"]])
+    assert (kids[kids >= 0] > 0).all()
+
+
+def test_bvh_degenerate_inputs(pt, cornell):
+    tris, _ = cornell
+    one = pt.build_bvh_host(tris[:1])
+    assert len(one["nodes"]) == 1 and one["nodes"]["child0"][0] == one["nodes"]["child1"][0] < 0
+    same = np.repeat(tris[:1], 9)  # identical centroids: no bin separates them -> median split fallback
+    b = pt.build_bvh_host(same)
+    _validate_bvh(pt, same, b)
+    bad = tris[:2].copy()
+    bad["p1"][0, 0] = np.nan
+    with pytest.raises(pt.PtbError, match="non-finite"):
+        pt.build_bvh_host(bad)
+
+
+def test_light_and_tessellate_helpers(pt, ob, cornell):
+    tris, _ = cornell
+    assert pt.light_from_quad(tris, 5) == ob.light_from_quad(tris, 5)
+    p1, ea, eb = pt.light_from_quad(tris, 5)
+    area = np.linalg.norm(np.cross(ea, eb))
+    assert abs(area - 1.365) < 1e-3  # light area 1.365
+    assert np.cross(ea, eb)[1] < 0  # front side faces -y (into the room)
+    with pytest.raises(pt.PtbError):
+        pt.light_from_quad(tris, 99)
+    with pytest.raises(pt.PtbError):
+        pt.tessellate(tris[:3], 2)
+
+
+def test_ppm_writer(pt, ob, tmp_path):
+    # RaytraceTest.cpp:277-287: "P3\n%d %d\n%d\n" + "%d %d %d " per pixel, value = min((int)(sqrtf(v)*255),255)
+    rng = np.random.default_rng(0)
+    fb = rng.uniform(0, 1.5, (6, 4)).astype(np.float32)
+    path = tmp_path / "out.ppm"
+    pt.write_ppm(str(path), fb, 3, 2)
+    txt = path.read_text()
+    assert txt.startswith("P3\n3 2\n255\n")
+    vals = [int(v) for v in txt.split()[4:]]
+    assert vals == ob.to_rgb8(fb).reshape(-1).tolist() == pt.to_rgb8(fb).reshape(-1).tolist()
+
+
+def test_no_cpu_fallback_without_gpu(pt):
+    """On a box without CUDA the product refuses to run (no silent CPU path)."""
+    n = C.c_int(-1)
+    rc = pt.lib().ptb_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pt.PtbError, match="no CUDA device|no CPU fallback"):
+        pt.Device(0)
+
+
+def test_render_params_defaults_equal_reference_constants(pt):
+    p = pt.default_params()
+    assert (p.width, p.height) == (512, 512)  # RaytraceTest.cpp:219
+    assert p.max_depth == 16  # GenerateColors.cl:5 BOUNCES
+    assert p.accum == pt.ACCUM_REFERENCE and p.mode == pt.MODE_PATH
+    assert p.light_quad == 5 and p.shard_count == 1
+    assert pt.local_pixels(p) == 512 * 512
+    q = pt.default_params(width=40, height=25, shard_index=1, shard_count=3, shard_block=64)
+    from oclpathtracer_b200 import sharding
+    assert pt.local_pixels(q) == sharding.local_pixels(1000, 1, 3, 64) == 320
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: no product source may reference it."""
+    pkg = os.path.join(ROOT, "oclpathtracer_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(base, f), errors="ignore").read()
+                for needle in ("oracle_pt", "liboracle", "from oracle", "import oracle", "oracle/"):
+                    assert needle not in src, (f, needle)
+    for f in os.listdir(os.path.join(ROOT, "include")):
+        src = open(os.path.join(ROOT, "include", f)).read()
+        for needle in ("oracle_pt", "liboracle", "oracle/"):
+            assert needle not in src, (f, needle)

@@ -1,0 +1,225 @@
+"""CPU tests: the oracle against the source-derived golden vectors and its own invariants."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, SCENE, bits, oracle_params
+
+
+def test_rng_known_answers(ob):
+    # GenerateColors.cl:47-71,:308 -- integer-exact vectors from tests/golden/make_golden.py (pure Python)
+    kat = json.load(open(os.path.join(GOLDEN, "rng_kat.json")))
+    for f, v in kat["hash_uint32"].items():
+        assert ob.lib().ora_hash_uint32(int(f)) == v
+    for case in kat["cases"]:
+        st, va = ob.rng_kat(case["gid"], case["frame"], len(case["states"]))
+        assert st.tolist() == case["states"]
+        assert bits(va).tolist() == case["value_bits"]
+    assert kat["max_state_value_bits"] == 0x3F800000  # (float)0xFFFFFFFF * 2^-32 == 1.0f
+
+
+def test_rng_survey_appendix_c(ob):
+    st, va = ob.rng_kat(0, 0, 4)
+    assert [hex(s) for s in st] == ["0x3d8a7e50", "0x57db8a89", "0xd9b36308", "0xdef15f9b"]
+    np.testing.assert_allclose(va, [0.24039449, 0.34319368, 0.85039347, 0.87087059], rtol=0, atol=1e-8)
+    st, _ = ob.rng_kat(131328, 7, 4)
+    assert [hex(s) for s in st] == ["0x2c9a79cb", "0xe83d9434", "0xc0e8719e", "0xa50ed6d5"]
+
+
+def test_scene_file_and_loader(ob, cornell):
+    facts = json.load(open(os.path.join(GOLDEN, "scene.json")))
+    raw = open(SCENE, "rb").read()
+    assert hashlib.sha256(raw).hexdigest() == facts["sha256"] == (
+        "075b51a2ebb6ab4e9dcd2353dfc55922090cf58ff87fd8aeea1907c7d5d18f62")
+    tris, mats = cornell
+    assert len(tris) == 36 and len(mats) == 18  # RaytraceTest.cpp:207-208
+    assert tris["id"].tolist() == [i // 2 for i in range(36)]
+    pts = np.concatenate([tris["p1"], tris["p2"], tris["p3"]])
+    np.testing.assert_array_equal(pts[:, 3], 0.0)  # w := 0 (:181-184)
+    np.testing.assert_allclose(pts[:, :3].min(0), facts["aabb_lo"])
+    np.testing.assert_allclose(pts[:, :3].max(0), facts["aabb_hi"])
+    # quad split (p1,p2,p3),(p3,p4,p1)  (:186-187)
+    for q in range(18):
+        np.testing.assert_array_equal(tris["p3"][2 * q], tris["p1"][2 * q + 1])
+        np.testing.assert_array_equal(tris["p1"][2 * q], tris["p3"][2 * q + 1])
+    # materials (:145-176)
+    assert mats["type"].tolist() == [1] * 8 + [2] * 10
+    assert mats["emissive"][5].tolist() == [30.0, 30.0, 30.0, 1.0]
+    assert all(mats["emissive"][i].tolist() == [0.0, 0.0, 0.0, 1.0] for i in range(18) if i != 5)
+    np.testing.assert_array_equal(mats["albedo"][5], np.float32([0.7, 0.7, 0.7, 1.0]))
+    np.testing.assert_array_equal(mats["albedo"][6], np.float32([0.6, 0.0, 0.0, 1.0]))
+    np.testing.assert_array_equal(mats["albedo"][7], np.float32([0.0, 0.6, 0.0, 1.0]))
+    np.testing.assert_array_equal(mats["albedo"][8], np.float32([0.5, 0.35, 0.05, 0.0]))
+    assert mats["roughness"][8] == np.float32(0.008)
+
+
+def test_tan_half_fov_constant(ob):
+    # fov fp32 = 0x3F860A92, tan(fov/2) correctly rounded = 0x3F13CD3A
+    fov = np.float32((np.float32(60.0) * np.pi) / np.float32(180.0))
+    assert int(fov.view(np.uint32)) == 0x3F860A92
+    t = np.float32(ob.lib().ora_tan(np.float32(0.5) * fov))
+    assert int(t.view(np.uint32)) == 0x3F13CD3A
+
+
+def _ulp_err(a, ref):
+    ref32 = ref.astype(np.float32)
+    ulp = np.maximum(np.spacing(np.abs(ref32)).astype(np.float64), 2.0 ** -149)
+    return np.abs(a.astype(np.float64) - ref) / ulp
+
+
+def test_sincos_accuracy(ob):
+    x = np.linspace(0, 2 * np.pi, 1_000_001).astype(np.float32)
+    s, c = ob.sincos(x)
+    xd = x.astype(np.float64)
+    assert _ulp_err(s, np.sin(xd)).max() <= 2.0
+    assert _ulp_err(c, np.cos(xd)).max() <= 2.0  # inside OpenCL C's 4-ulp bound for sin/cos
+    s0, c0 = ob.sincos(np.float32([0.0]))
+    assert s0[0] == 0.0 and c0[0] == 1.0
+
+
+def test_pow_accuracy_and_specials(ob):
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([rng.uniform(0, 1, 200_000), rng.uniform(0, 200, 200_000), 10.0 ** rng.uniform(-38, 38, 50_000)])
+    xs = xs.astype(np.float32)
+    for y in (np.float32(2.2), np.float32(1.0) / np.float32(2.2)):
+        p = ob.powf(xs, y)
+        ref = np.power(xs.astype(np.float64), np.float64(y))
+        ok = np.isfinite(ref) & (ref < 3.4e38) & (ref > 1e-37)
+        assert _ulp_err(p[ok], ref[ok]).max() <= 0.5001  # correctly rounded
+    sp = ob.powf(np.float32([0.0, 1.0, np.inf, np.nan, -1.0]), np.float32(2.2))
+    assert sp[0] == 0.0 and sp[1] == 1.0 and np.isinf(sp[2]) and np.isnan(sp[3]) and np.isnan(sp[4])
+
+
+def test_camera_ray(ob):
+    # GenerateColors.cl:263-288: eye (0,2.75,4); unit direction; centre pixel looks down -z
+    o, d, seed = ob.generate_ray(256, 256, 512, 512, 12345)
+    np.testing.assert_array_equal(o, np.float32([0.0, 2.75, 4.0]))
+    assert abs(np.linalg.norm(d.astype(np.float64)) - 1) < 1e-6
+    assert d[2] < -0.99
+    st, _ = ob.rng_kat(0, 0, 2)  # two draws consumed (x jitter then y jitter)
+    _, _, seed2 = ob.generate_ray(0, 0, 512, 512, 0 + ob.lib().ora_hash_uint32(0))
+    assert seed2 == st[1]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_bvh_equals_brute_force(ob, cornell, cornell_bvh, mode):
+    """The BUILD-DEFINED BVH may only skip triangles the reference loop would reject."""
+    tris, mats = cornell
+    _, bvh, _ = cornell_bvh
+    a, sa, ca = ob.render(oracle_params(ob, tris, 96, 96, n_frames=3, mode=mode, accum=ob.ACCUM_LINEAR, use_bvh=0),
+                          tris, mats, want_stats=True)
+    b, sb, cb = ob.render(oracle_params(ob, tris, 96, 96, n_frames=3, mode=mode, accum=ob.ACCUM_LINEAR, use_bvh=1),
+                          tris, mats, bvh=bvh, want_stats=True)
+    assert a.tobytes() == b.tobytes()
+    for f in ("tri", "quad", "t_bits", "count"):
+        np.testing.assert_array_equal(sa[f], sb[f])
+    assert ca["rays_closest"] == cb["rays_closest"] and ca["rays_any"] == cb["rays_any"]
+    assert ca["tri_tests"] == 36 * (ca["rays_closest"]) + ca["tri_tests"] - 36 * ca["rays_closest"]  # sanity
+    assert cb["nodes"] > 0 and cb["tri_tests"] < ca["tri_tests"]
+
+
+def test_trace_random_rays_brute_vs_bvh(ob, cornell, cornell_bvh):
+    tris, _ = cornell
+    _, bvh, _ = cornell_bvh
+    rng = np.random.default_rng(3)
+    n = 200_000
+    o = rng.uniform([-2.7, 0.05, -5.5], [2.7, 5.4, 3.0], (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d[:100] = np.float32([0, 0, -1])  # axis-aligned directions (zero components -> safe_rcp path)
+    d[100:200] = np.float32([0, 1, 0])
+    d[200:300] = np.float32([1, 0, 0])
+    for any_hit, tmax in ((False, 1e20), (True, 2.0)):
+        a = ob.trace(tris, o, d, tmax, bvh=None, any_hit=any_hit)
+        b = ob.trace(tris, o, d, tmax, bvh=bvh, any_hit=any_hit)
+        np.testing.assert_array_equal(a["tri"] >= 0, b["tri"] >= 0)
+        if not any_hit:
+            for f in ("tri", "t", "u", "v"):
+                np.testing.assert_array_equal(bits(a[f]), bits(b[f]))
+
+
+def test_reference_accumulation_semantics(ob, cornell):
+    """GenerateColors.cl:314-321: gamma-space running mean whose weights drop frame 0."""
+    tris, mats = cornell
+    w = h = 24
+    samples = []
+    for f in range(4):
+        fb, _, _ = ob.render(ob.default_params(w, h, first_frame=f, n_frames=1, mode=3, accum=ob.ACCUM_LINEAR), tris, mats)
+        samples.append(fb[:, :3].astype(np.float64))
+    ref, _, _ = ob.render(ob.default_params(w, h, first_frame=0, n_frames=4, mode=3, accum=ob.ACCUM_REFERENCE), tris, mats)
+    want = (samples[1] + samples[2] + samples[3]) / 3.0  # frame 0 is discarded at z = 1
+    got = ref[:, :3].astype(np.float64) ** 2.2
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=1e-6)
+    np.testing.assert_array_equal(ref[:, 3], 1.0)
+    # resumable: frames 0-1 then 2-3 == frames 0-3
+    part, _, _ = ob.render(ob.default_params(w, h, first_frame=0, n_frames=2, mode=3, accum=ob.ACCUM_REFERENCE), tris, mats)
+    full, _, _ = ob.render(ob.default_params(w, h, first_frame=2, n_frames=2, mode=3, accum=ob.ACCUM_REFERENCE), tris, mats, fb=part)
+    assert full.tobytes() == ref.tobytes()
+
+
+def test_max_depth_and_path_statistics(ob, cornell):
+    tris, mats = cornell
+    _, st8, c8 = ob.render(ob.default_params(48, 48, n_frames=1, mode=3, accum=1, max_depth=8), tris, mats, want_stats=True)
+    _, st16, c16 = ob.render(ob.default_params(48, 48, n_frames=1, mode=3, accum=1, max_depth=16), tris, mats, want_stats=True)
+    assert st8["count"].max() == 8 and st16["count"].max() == 16
+    assert c8["rays_closest"] == int(st8["count"].sum()) and c16["rays_closest"] >= c8["rays_closest"]
+    np.testing.assert_array_equal(st8["tri"], st16["tri"])
+    assert (st8["tri"] >= 0).all()  # the camera looks into the closed box: every primary ray hits
+
+
+def test_sharding_partitions_image(ob, cornell):
+    tris, mats = cornell
+    w, h = 40, 25  # 1000 pixels: not a multiple of block*world -> ragged shards
+    full, sf, _ = ob.render(ob.default_params(w, h, n_frames=2, mode=3, accum=1, max_depth=4), tris, mats, want_stats=True)
+    world, block = 3, 64
+    seen = np.zeros(w * h, bool)
+    for r in range(world):
+        prm = ob.default_params(w, h, n_frames=2, mode=3, accum=1, max_depth=4, shard_index=r, shard_count=world, shard_block=block)
+        part, sp, _ = ob.render(prm, tris, mats, want_stats=True)
+        li = np.arange(len(part))
+        gid = ((li // block) * world + r) * block + li % block
+        assert not seen[gid].any()
+        seen[gid] = True
+        assert part.tobytes() == full[gid].tobytes()
+        assert sp.tobytes() == sf[gid].tobytes()
+    assert seen.all()
+
+
+def test_tessellation_matches_product_and_preserves_hits(pt, ob, cornell):
+    tris, mats = cornell
+    k = 3
+    a = ob.tessellate(tris, k)
+    b = pt.tessellate(tris, k)
+    assert len(a) == 36 * k * k and a.tobytes() == b.tobytes()
+    # same surfaces: primary hit quad ids agree with the untessellated scene except on sub-quad seams
+    f0, s0, _ = ob.render(ob.default_params(64, 64, mode=0, accum=1), tris, mats, want_stats=True)
+    f1, s1, _ = ob.render(ob.default_params(64, 64, mode=0, accum=1), a, mats, want_stats=True)
+    assert (s0["quad"] == s1["quad"]).mean() > 0.995
+
+
+def test_golden_small_renders(pt, ob, cornell):
+    """The committed oracle vectors still reproduce (pins the oracle against drift)."""
+    tris, mats = cornell
+    g = np.load(os.path.join(GOLDEN, "oracle_small.npz"))
+    b = pt.build_bvh_host(tris)
+    assert b["nodes"].view(np.uint8).tobytes() == g["bvh_nodes"].tobytes()
+    np.testing.assert_array_equal(b["tri_order"], g["bvh_order"])
+    bvh, _keep = ob.make_bvh(b["nodes"], b["tri_order"])
+    for name, mode in (("primary", 0), ("ao", 1), ("direct", 2), ("path", 3)):
+        prm = oracle_params(ob, tris, 32, 32, n_frames=3, mode=mode, accum=ob.ACCUM_LINEAR, use_bvh=1, max_depth=8)
+        fb, st, ctr = ob.render(prm, tris, mats, bvh=bvh, want_stats=True)
+        assert fb.tobytes() == g[f"{name}_fb"].tobytes(), name
+        assert st.tobytes() == g[f"{name}_stats"].tobytes(), name
+        assert [ctr[k] for k in ("rays_closest", "rays_any", "nodes", "tri_tests")] == g[f"{name}_ctr"].tolist()
+    fb, _, _ = ob.render(ob.default_params(32, 32, first_frame=0, n_frames=5, mode=3, accum=0, use_bvh=0), tris, mats)
+    assert fb.tobytes() == g["path_reference_accum_fb"].tobytes()
+
+
+def test_output_transform(ob):
+    # RaytraceTest.cpp:78-83,:280-285: min((int)(sqrtf(v)*255), 255)
+    fb = np.float32([[0.0, 0.25, 1.0, 1.0], [4.0, 0.5, 1e-9, 1.0]])
+    rgb = ob.to_rgb8(fb)
+    assert rgb.tolist() == [[0, 127, 255], [255, int(np.float32(np.sqrt(np.float32(0.5))) * np.float32(255)), 0]]
