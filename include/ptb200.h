@@ -156,6 +156,16 @@ int ptb_render_host(ptb_device* dev, const ptb_triangle* tris, int n_tris, const
                     const ptb_render_params* params, float* out_rgba, ptb_pixel_stats* out_stats,
                     ptb_counters* counters);
 
+/* ---- measurement hooks ----------------------------------------------------------------
+ * (the reference's analogue: Device::toggleProfiling + the ms launch1D returns,
+ * Adl/Adl.h:143-171, Adl/CL/AdlKernelUtilsCL.cpp:470-499).  With profiling on, every
+ * render batch is bracketed by CUDA events on the device's stream; _read synchronises
+ * and returns the totals since the previous read.  kernel_launches counts this
+ * library's own kernel launches (always on).                                      */
+int ptb_device_profile(ptb_device* dev, int enable);
+int ptb_device_profile_read(ptb_device* dev, float* integrator_ms, float* resolve_ms, int* integrator_launches,
+                            uint64_t* kernel_launches);
+
 /* ---- unit access for parity tests -----------------------------------------------------
  * scene query on caller-supplied rays (host arrays: o, d = 3 floats per ray).   */
 int ptb_trace(ptb_device* dev, ptb_scene* scene, int accel, int any_hit, int n_rays, const float* o,

@@ -56,6 +56,12 @@ struct ptb_device {
     ptb_buffer* host_tris = nullptr; ptb_buffer* host_mats = nullptr;
     ptb_buffer* host_frame = nullptr; ptb_buffer* host_stats = nullptr;
     void* pinned = nullptr; size_t pinned_bytes = 0;
+    // measurement
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;   // triples: before integrator, after integrator, after resolve
+    size_t ev_used = 0;
+    int integrator_launch_batches = 0;
+    uint64_t kernel_launches = 0;
 };
 
 struct ptb_buffer {
@@ -187,6 +193,7 @@ extern "C" int ptb_device_destroy(ptb_device* dev) {
     if (dev->wf) cudaFree(dev->wf);
     if (dev->counters) cudaFree(dev->counters);
     if (dev->pinned) cudaFreeHost(dev->pinned);
+    for (cudaEvent_t e : dev->ev_pool) cudaEventDestroy(e);
     if (dev->own_stream && dev->stream) cudaStreamDestroy(dev->stream);
     int leaked = dev->live_buffers;
     delete dev;
@@ -540,13 +547,29 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
         const int nb = (p->n_frames - f0 < fpb) ? p->n_frames - f0 : fpb;
         a.first_frame = p->first_frame + f0;
         a.frames_in_batch = nb;
+        cudaEvent_t* ev = nullptr;
+        if (dev->profiling) {
+            if (dev->ev_used + 3 > dev->ev_pool.size()) {
+                for (int k = 0; k < 3; ++k) {
+                    cudaEvent_t e;
+                    CU_TRY(cudaEventCreate(&e));
+                    dev->ev_pool.push_back(e);
+                }
+            }
+            ev = &dev->ev_pool[dev->ev_used];
+            dev->ev_used += 3;
+            CU_TRY(cudaEventRecord(ev[0], dev->stream));
+        }
         if (integrator == PTB_INTEGRATOR_WAVEFRONT) {
             if (int rc = ptd::wavefront_render(dev->stream, &dev->wf, &dev->wf_bytes, dev->counters, p->mode, sc, a, bvh, small, stats,
-                                               dev->prop.multiProcessorCount))
+                                               dev->prop.multiProcessorCount, &dev->kernel_launches))
                 return rc;
         } else {
             if (int rc = launch_mega(dev, p->mode, sc, a, bvh, small, stats)) return rc;
+            dev->kernel_launches += 1;
         }
+        if (ev) CU_TRY(cudaEventRecord(ev[1], dev->stream));
+        dev->integrator_launch_batches++;
         ptd::ResolveArgs r;
         r.samples = a.samples; r.n_local = n_local; r.frames_in_batch = nb; r.first_frame = a.first_frame;
         r.accum = p->accum; r.first_batch = f0 == 0; r.last_batch = f0 + nb >= p->n_frames;
@@ -554,6 +577,8 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
         r.sum = static_cast<float4*>(dev->sum); r.frame = d_frame;
         ptd::k_resolve<<<(n_local + 255) / 256, 256, 0, dev->stream>>>(r);
         CU_TRY(cudaGetLastError());
+        dev->kernel_launches += 1;
+        if (ev) CU_TRY(cudaEventRecord(ev[2], dev->stream));
     }
     if (counters) {
         unsigned long long h[ptd::CTR_COUNT];
@@ -720,6 +745,36 @@ extern "C" int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* b
     p.mode = PTB_MODE_PATH; p.accum = PTB_ACCUM_REFERENCE;
     p.max_depth = k->bounces; p.accel = k->accel; p.integrator = k->integrator;
     return render_impl(dev, k->scene, &p, static_cast<float4*>(fb->d_ptr), fb->bytes, nullptr, 0, nullptr);
+}
+
+// ---- measurement hooks -----------------------------------------------------------------------------------------
+
+extern "C" int ptb_device_profile(ptb_device* dev, int enable) {
+    if (!dev) return fail(PTB_E_INVALID, "ptb_device_profile: null device");
+    dev->profiling = enable != 0;
+    return PTB_OK;
+}
+
+extern "C" int ptb_device_profile_read(ptb_device* dev, float* integrator_ms, float* resolve_ms, int* integrator_launches,
+                                       uint64_t* kernel_launches) {
+    if (!dev) return fail(PTB_E_INVALID, "ptb_device_profile_read: null device");
+    if (set_device(dev)) return PTB_E_CUDA;
+    CU_TRY(cudaStreamSynchronize(dev->stream));
+    float ti = 0.f, tr = 0.f;
+    for (size_t k = 0; k + 2 < dev->ev_used + 0 && k + 2 < dev->ev_pool.size() + 0; k += 3) {
+        float a = 0.f, b = 0.f;
+        CU_TRY(cudaEventElapsedTime(&a, dev->ev_pool[k], dev->ev_pool[k + 1]));
+        CU_TRY(cudaEventElapsedTime(&b, dev->ev_pool[k + 1], dev->ev_pool[k + 2]));
+        ti += a; tr += b;
+    }
+    if (integrator_ms) *integrator_ms = ti;
+    if (resolve_ms) *resolve_ms = tr;
+    if (integrator_launches) *integrator_launches = dev->integrator_launch_batches;
+    if (kernel_launches) *kernel_launches = dev->kernel_launches;
+    dev->ev_used = 0;
+    dev->integrator_launch_batches = 0;
+    dev->kernel_launches = 0;
+    return PTB_OK;
 }
 
 // ---- unit access for parity tests -----------------------------------------------------------------------------

@@ -404,7 +404,7 @@ static int wf_smem(K kernel, size_t smem) {
 
 template <bool BVH, bool SMALL, bool STATS>
 static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArgs& a, const WfBuffers& w,
-                  unsigned long long* counters) {
+                  unsigned long long* counters, uint64_t* launches) {
     const long long P = (long long)a.frames_in_batch * a.n_local;
     const int block = 128;
     const unsigned grid = (unsigned)((P + block - 1) / block);
@@ -413,6 +413,7 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
     int rc;
     wf_generate<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(a, w, STATS ? 1 : 0);
     WF_TRY(cudaGetLastError());
+    *launches += 1;
     auto ext = wf_extend<BVH, SMALL, STATS>;
     if ((rc = wf_smem(ext, smem_q))) return rc;
     if (mode == PTB_MODE_PATH) {
@@ -422,11 +423,13 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
             const int qi = depth & 1;
             ext<<<grid, block, smem_q, st>>>(sc, w, depth, qi, counters);
             shade<<<grid, block, smem_s, st>>>(sc, a, w, depth, qi);
+            *launches += 2;
         }
         WF_TRY(cudaGetLastError());
     } else {
         ext<<<grid, block, smem_q, st>>>(sc, w, 0, 0, counters);
         WF_TRY(cudaGetLastError());
+        *launches += mode == PTB_MODE_PRIMARY ? 2 : (mode == PTB_MODE_AO ? 4 : 3);
         if (mode == PTB_MODE_PRIMARY) {
             auto k = wf_shade_first<PTB_MODE_PRIMARY, BVH, SMALL, STATS>;
             if ((rc = wf_smem(k, smem_s))) return rc;
@@ -453,6 +456,7 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
     if (STATS && a.stats) {
         wf_export_stats<<<(a.n_local + 255) / 256, 256, 0, st>>>(a, w);
         WF_TRY(cudaGetLastError());
+        *launches += 1;
     }
     return 0;
 }
@@ -460,7 +464,7 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
 // scratch layout for one batch; (re)allocates *scratch when it is too small
 static int wavefront_render(cudaStream_t st, void** scratch, size_t* scratch_bytes, unsigned long long* counters,
                             int mode, const SceneDev& sc, const RenderArgs& a, bool bvh, bool small, bool stats,
-                            int /*sm_count*/) {
+                            int /*sm_count*/, uint64_t* launches) {
     const size_t P = (size_t)a.frames_in_batch * a.n_local;
     const size_t n_shadow = mode == PTB_MODE_AO ? P * (size_t)a.ao_samples : (mode == PTB_MODE_DIRECT ? P : 0);
     const size_t n_counts = (size_t)a.max_depth + 2;
@@ -498,7 +502,7 @@ static int wavefront_render(cudaStream_t st, void** scratch, size_t* scratch_byt
     w.slot_stats = (ptb_pixel_stats*)(base + o_stats);
     w.counts = (unsigned int*)(base + o_counts);
     WF_TRY(cudaMemsetAsync(w.counts, 0, n_counts * 4, st));
-#define WF_CASE(B, S, T) if (bvh == B && small == S && stats == T) return wf_run<B, S, T>(st, mode, sc, a, w, counters)
+#define WF_CASE(B, S, T) if (bvh == B && small == S && stats == T) return wf_run<B, S, T>(st, mode, sc, a, w, counters, launches)
     WF_CASE(true, true, false); WF_CASE(true, true, true); WF_CASE(true, false, false); WF_CASE(true, false, true);
     WF_CASE(false, true, false); WF_CASE(false, true, true); WF_CASE(false, false, false); WF_CASE(false, false, true);
 #undef WF_CASE

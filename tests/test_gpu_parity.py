@@ -233,8 +233,10 @@ def test_sharded_render_is_bit_identical(dev, pt, ob, cornell, scene):
 def test_single_triangle_and_miss_paths(dev, pt, ob, cornell):
     tris, mats = cornell
     one = tris[10:11].copy()  # half of the light, seen from below
+    p1, ea, eb = pt.light_from_quad(tris, 5)
     for mode in (0, 1, 2, 3):
-        prm = pt.default_params(width=64, height=64, n_frames=2, mode=mode, accum=pt.ACCUM_LINEAR, max_depth=4, collect_stats=1)
+        prm = pt.default_params(width=64, height=64, n_frames=2, mode=mode, accum=pt.ACCUM_LINEAR, max_depth=4, collect_stats=1,
+                                light_p1=p1, light_ea=ea, light_eb=eb)
         for integ in (pt.INTEGRATOR_MEGAKERNEL, pt.INTEGRATOR_WAVEFRONT):
             prm.integrator = integ
             fb, st, ctr = dev.render_host(one, mats, prm, want_stats=True)
