@@ -1,0 +1,175 @@
+// Adl/Adl.h -- ADL-shaped C++ shim over the ptb200 C-ABI.
+//
+// Provides the subset of the reference's ADL API that its ray-cast flow uses
+// (test/RaytraceTest.cpp:202-291), with the same names and argument meaning, so a
+// maintainer can point that flow at libptb200.so by switching the include path:
+//   adl::init / adl::quit                      (reference Adl/Adl.h:96-98)
+//   adl::DeviceUtils::allocate / deallocate / waitForCompletion   (Adl/Adl.h:100-131)
+//   adl::Device::getKernel / getDeviceVersion  (Adl/Adl.h:164-166)
+//   adl::Buffer<T>                             (Adl/Adl.h:203-265)
+//   adl::BufferInfo, adl::Launcher             (Adl/AdlKernel.h:94-202)
+// Error convention: like release-mode ADL nothing throws; failures leave null
+// handles / zero sizes and the message is available from ptb_last_error().
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+#include "ptb200.h"
+
+namespace adl {
+
+typedef unsigned long long adlu64;
+
+enum DeviceType { TYPE_CL = 0, TYPE_DX11 = 1, TYPE_HOST = 2, TYPE_METAL = 3, TYPE_VULKAN = 4, TYPE_CUDA = 5 };
+
+inline bool init(DeviceType) {
+    int n = 0;
+    return ptb_device_count(&n) == PTB_OK && n > 0;
+}
+inline void quit(DeviceType) {}
+
+struct Kernel {
+    ptb_kernel* m_kernel = nullptr;
+};
+
+class Device {
+  public:
+    explicit Device(ptb_device* d) : m_type(TYPE_CUDA), m_dev(d) {}
+    // name -> kernel, cached by the device for its lifetime; null when unknown
+    const Kernel* getKernel(const char* fileName, const char* funcName, const char* /*option*/ = nullptr) const {
+        for (int i = 0; i < m_nKernels; ++i)
+            if (!std::strcmp(m_names[i], funcName)) return &m_kernels[i];
+        ptb_kernel* k = nullptr;
+        if (ptb_kernel_get(m_dev, fileName, funcName, &k) != PTB_OK || m_nKernels == kMaxKernels) return nullptr;
+        std::strncpy(m_names[m_nKernels], funcName, sizeof m_names[0] - 1);
+        m_kernels[m_nKernels].m_kernel = k;
+        return &m_kernels[m_nKernels++];
+    }
+    void getDeviceVersion(char nameOut[128]) const { ptb_device_name(m_dev, nameOut); }
+    void getDeviceName(char nameOut[128]) const { ptb_device_name(m_dev, nameOut); }
+    DeviceType m_type;
+    ptb_device* m_dev;
+
+  private:
+    enum { kMaxKernels = 8 };
+    mutable Kernel m_kernels[kMaxKernels];
+    mutable char m_names[kMaxKernels][64] = {};
+    mutable int m_nKernels = 0;
+};
+
+class DeviceUtils {
+  public:
+    struct Config {
+        enum DeviceType { DEVICE_GPU, DEVICE_CPU };
+        Config() : m_type(DEVICE_GPU), m_deviceIdx(0) {}
+        DeviceType m_type;
+        int m_deviceIdx;
+    };
+    static int getNDevices(DeviceType) {
+        int n = 0;
+        ptb_device_count(&n);
+        return n;
+    }
+    // returns 0 when no device can be created (the reference returns a half-initialised object instead)
+    static Device* allocate(DeviceType, Config cfg = Config()) {
+        ptb_device* d = nullptr;
+        if (ptb_device_create(cfg.m_deviceIdx, &d) != PTB_OK) return nullptr;
+        return new Device(d);
+    }
+    static void deallocate(Device* device) {
+        if (!device) return;
+        ptb_device_destroy(device->m_dev);
+        delete device;
+    }
+    static void waitForCompletion(const Device* device) {
+        if (device) ptb_device_sync(device->m_dev);
+    }
+};
+
+struct BufferBase {
+    enum BufferType { BUFFER, BUFFER_CONST, BUFFER_STAGING, BUFFER_APPEND, BUFFER_RAW, BUFFER_W_COUNTER, BUFFER_INDEX, BUFFER_VERTEX, BUFFER_ZERO_COPY };
+};
+
+template <typename T>
+struct Buffer : public BufferBase {
+    Buffer() : m_device(nullptr), m_size(0), m_buf(nullptr) {}
+    Buffer(const Device* device, adlu64 nElems, BufferType = BUFFER) : m_device(nullptr), m_size(0), m_buf(nullptr) { allocate(device, nElems); }
+    virtual ~Buffer() {
+        if (m_buf) ptb_buffer_destroy(m_buf);
+    }
+    Buffer(const Buffer&) = delete;
+    Buffer& operator=(const Buffer&) = delete;
+    void allocate(const Device* device, adlu64 nElems, BufferType = BUFFER) {
+        m_device = device;
+        // on failure: null handle and zero size, no throw (Adl/CL/AdlCL.inl:190-197)
+        m_size = (device && ptb_buffer_create(device->m_dev, size_t(nElems) * sizeof(T), &m_buf) == PTB_OK) ? nElems : 0;
+    }
+    void write(const T* hostSrcPtr, adlu64 nElems, adlu64 dstOffsetNElems = 0) {
+        if (m_buf) ptb_buffer_write(m_buf, hostSrcPtr, size_t(nElems) * sizeof(T), size_t(dstOffsetNElems) * sizeof(T));
+    }
+    void read(T* hostDstPtr, adlu64 nElems, adlu64 srcOffsetNElems = 0) const {
+        if (m_buf) ptb_buffer_read(m_buf, hostDstPtr, size_t(nElems) * sizeof(T), size_t(srcOffsetNElems) * sizeof(T));
+    }
+    void clear() {
+        if (m_buf) ptb_buffer_clear(m_buf);
+    }
+    // map the whole buffer read/write; contents are valid after waitForCompletion
+    T* getHostPtr(adlu64 /*size*/ = adlu64(-1), bool /*blocking*/ = false) const {
+        void* p = nullptr;
+        return (m_buf && ptb_buffer_map(m_buf, &p) == PTB_OK) ? static_cast<T*>(p) : nullptr;
+    }
+    void returnHostPtr(T* ptr) const {
+        if (m_buf && ptr) ptb_buffer_unmap(m_buf, ptr);
+    }
+    adlu64 getSize() const { return m_size; }
+
+    const Device* m_device;
+    adlu64 m_size;
+    ptb_buffer* m_buf;
+};
+
+struct BufferInfo {
+    BufferInfo() : m_buffer(nullptr), m_isReadOnly(false) {}
+    template <typename T>
+    BufferInfo(const Buffer<T>* buff, bool isReadOnly = false) : m_buffer(buff ? buff->m_buf : nullptr), m_isReadOnly(isReadOnly) {}
+    ptb_buffer* m_buffer;
+    bool m_isReadOnly;
+};
+
+#define ADL_DEFAULT_LOCAL_SIZE_1D 64
+
+class Launcher {
+  public:
+    enum { MAX_ARG_SIZE = 64, MAX_ARG_COUNT = 64 };
+    Launcher(const Device* dd, const Kernel* kernel) : m_deviceData(dd), m_kernel(kernel), m_nBufs(0), m_constBytes(0) {}
+    // positional arguments: buffers first, then by-value constants (auto-incrementing index)
+    void setBuffers(BufferInfo* buffInfo, int n) {
+        for (int i = 0; i < n && m_nBufs < MAX_ARG_COUNT; ++i) m_bufs[m_nBufs++] = buffInfo[i].m_buffer;
+    }
+    template <typename T>
+    void setConst(const T& consts) {
+        static_assert(sizeof(T) <= MAX_ARG_SIZE, "constant block too large");
+        std::memcpy(m_const, &consts, sizeof(T));
+        m_constBytes = sizeof(T);
+    }
+    // returns 0 (the reference returns elapsed ms only in profiling builds)
+    float launch1D(int numThreads, int localSize = ADL_DEFAULT_LOCAL_SIZE_1D) {
+        if (m_deviceData && m_kernel)
+            ptb_launch1d(m_deviceData->m_dev, m_kernel->m_kernel, m_bufs, m_nBufs, m_const, m_constBytes, numThreads, localSize);
+        return 0.f;
+    }
+
+  private:
+    const Device* m_deviceData;
+    const Kernel* m_kernel;
+    ptb_buffer* m_bufs[MAX_ARG_COUNT];
+    int m_nBufs;
+    unsigned char m_const[MAX_ARG_SIZE];
+    size_t m_constBytes;
+};
+
+}  // namespace adl
+
+#define SELECT_KERNELPATH1(device, path, name) (path "ClKernels/" name)

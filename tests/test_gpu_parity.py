@@ -370,3 +370,19 @@ def test_buffer_map_unmap_and_errors(dev, pt):
         finally:
             s.close()
     tiny.close()
+
+
+def test_cpp_raycast_flow_matches_oracle(ob, cornell, tmp_path):
+    """host/raycast_main.cpp = the reference's DeviceTest.RayCast flow over the ADL-shaped shim."""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oclpathtracer_b200", "host", "ptb_raycast")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    out = tmp_path / "rc.ppm"
+    r = subprocess.run([exe, SCENE, str(out), "64", "5"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    vals = [int(v) for v in out.read_text().split()[4:]]
+    tris, mats = cornell
+    want, _, _ = ob.render(ob.default_params(64, 64, first_frame=0, n_frames=5, mode=3, accum=ob.ACCUM_REFERENCE), tris, mats)
+    assert vals == ob.to_rgb8(want).reshape(-1).tolist()

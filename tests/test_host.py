@@ -180,3 +180,68 @@ def test_product_never_imports_oracle():
         src = open(os.path.join(ROOT, "include", f)).read()
         for needle in ("oracle_pt", "liboracle", "oracle/"):
             assert needle not in src, (f, needle)
+
+
+def test_raycast_host_program_refuses_without_gpu(pt):
+    """The C++ mirror of DeviceTest.RayCast (host/raycast_main.cpp) exits loudly when there is no device."""
+    import subprocess
+    exe = os.path.join(ROOT, "oclpathtracer_b200", "host", "ptb_raycast")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    n = C.c_int(-1)
+    if pt.lib().ptb_device_count(C.byref(n)) == 0 and n.value > 0:
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([exe, SCENE, "/tmp/unused.ppm", "32", "1"], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr
+
+
+def _gloo_worker(rank, world, port, w, h, block, q):
+    import torch
+    import torch.distributed as dist
+    from oracle import binding as ob
+    from oclpathtracer_b200 import sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tris, mats = ob.load_model(SCENE)
+    # each rank renders its shard (the oracle stands in for the GPU renderer on this CPU-only box)
+    prm = ob.default_params(w, h, n_frames=2, mode=3, accum=1, max_depth=4, shard_index=rank, shard_count=world,
+                            shard_block=block, n_threads=2)
+    local, _, _ = ob.render(prm, tris, mats)
+    assert local.shape[0] == sharding.local_pixels(w * h, rank, world, block)
+    img = sharding.gather_image(torch.from_numpy(local), w * h, rank, world, block)
+    # frame sharding (bench.py's weak-scaling path): reduce(sum) of per-rank linear accumulators
+    fr = ob.default_params(w, h, first_frame=rank, n_frames=1, mode=3, accum=1, max_depth=4, n_threads=2)
+    mine, _, _ = ob.render(fr, tris, mats)
+    acc = torch.from_numpy(mine.copy())
+    dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        q.put((img.numpy().tobytes(), acc.numpy().tobytes()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("w,h", [(64, 32), (40, 25)])
+def test_two_rank_gloo_shard_and_gather(ob, cornell, w, h):
+    """world_size-2 gloo: image sharding + all_gather reassembles the single-device image bit for bit;
+    frame sharding + reduce(sum) equals the sum of the two single frames."""
+    import socket
+    import torch.multiprocessing as mp
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, w, h, 64, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    img_bytes, acc_bytes = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    tris, mats = cornell
+    full, _, _ = ob.render(ob.default_params(w, h, n_frames=2, mode=3, accum=1, max_depth=4), tris, mats)
+    assert img_bytes == full.tobytes()
+    f0, _, _ = ob.render(ob.default_params(w, h, first_frame=0, n_frames=1, mode=3, accum=1, max_depth=4), tris, mats)
+    f1, _, _ = ob.render(ob.default_params(w, h, first_frame=1, n_frames=1, mode=3, accum=1, max_depth=4), tris, mats)
+    assert acc_bytes == (f0 + f1).tobytes()
