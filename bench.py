@@ -48,6 +48,10 @@ def parse():
     ap.add_argument("--accel", default="bvh", choices=["bvh", "brute"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tune", action="append", default=[], help="experiment knob index=value (ptb_device_set_tuning)")
+    ap.add_argument("--fpb", type=int, default=0, help="frames_per_batch override")
+    ap.add_argument("--smem-nodes", type=int, default=0, help="BVH nodes staged in shared memory (0 = default)")
+    ap.add_argument("--max-leaf", type=int, default=0, help="BVH max triangles per leaf (0 = default)")
     ap.add_argument("--ab", action="store_true", help="also time the other integrator and brute force (extra keys)")
     return ap.parse_args()
 
@@ -178,7 +182,7 @@ def run_reference_arm(args, rank, world):
     from oracle import binding as ob
 
     # one step = one bounded sample: a 512x512 frame of the workload (a quarter of C2's pixels)
-    sample_px = min(wl["width"] * wl["height"], 512 * 512) if not wl.get("tess") else 64 * 64
+    sample_px = min(wl["width"] * wl["height"], 512 * 512) if not wl.get("tess") else 16 * 16
     for _ in range(args.warmup):
         cpu_reference(wl, seconds_budget=0.0, sample_px=sample_px, max_frames=1)
     rays, secs = 0, 0.0
@@ -227,9 +231,19 @@ def main():
 
     stream = torch.cuda.current_stream()
     dev = pt.Device(local, stream=stream.cuda_stream)  # enqueue on torch's stream so torch events see the work
+    for kv in args.tune:
+        i, v = kv.split("=")
+        dev.set_tuning(int(i), int(v))
     tris, mats, light = load_scene(pt, wl)
     t0 = time.perf_counter()
-    scene = dev.scene(tris, mats)
+    bp = None
+    if args.smem_nodes or args.max_leaf:
+        bp = pt.bvh_params()
+        if args.smem_nodes:
+            bp.smem_nodes = args.smem_nodes
+        if args.max_leaf:
+            bp.max_leaf = args.max_leaf
+    scene = dev.scene(tris, mats, bp)
     dev.sync()
     build_s = time.perf_counter() - t0
     npix = wl["width"] * wl["height"]
@@ -239,7 +253,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
 
     def params(step_frame, **kw):
-        return make_params(pt, wl, first_frame=step_frame, integrator=integ, accel=accel,
+        return make_params(pt, wl, first_frame=step_frame, integrator=integ, accel=accel, frames_per_batch=args.fpb,
                            light_p1=light[0], light_ea=light[1], light_eb=light[2], **kw)
 
     def step(i, profile_ctr=None):
@@ -345,7 +359,7 @@ def main():
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference(wl, seconds_budget=12.0, sample_px=None if not wl.get("tess") else 64 * 64, max_frames=4)
+        cpu = cpu_reference(wl, seconds_budget=12.0, sample_px=None if not wl.get("tess") else 16 * 16, max_frames=64)
         from oracle import binding as ob
         # stage counts of the BVH path at reduced size -> fp32 lane-ops per ray (SURVEY 8d formula)
         otris, omats = ob.load_model(SCENE)
@@ -368,9 +382,11 @@ def main():
     ab = None
     if args.ab and world == 1:
         ab = {}
-        for name, kw in (("megakernel_bvh", dict(integrator=pt.INTEGRATOR_MEGAKERNEL, accel=pt.ACCEL_BVH)),
-                         ("wavefront_bvh", dict(integrator=pt.INTEGRATOR_WAVEFRONT, accel=pt.ACCEL_BVH)),
-                         ("megakernel_brute", dict(integrator=pt.INTEGRATOR_MEGAKERNEL, accel=pt.ACCEL_BRUTE))):
+        variants = [("megakernel_bvh", dict(integrator=pt.INTEGRATOR_MEGAKERNEL, accel=pt.ACCEL_BVH)),
+                    ("wavefront_bvh", dict(integrator=pt.INTEGRATOR_WAVEFRONT, accel=pt.ACCEL_BVH))]
+        if len(tris) <= 4096:  # the reference's brute-force loop is O(triangles) per ray
+            variants.append(("megakernel_brute", dict(integrator=pt.INTEGRATOR_MEGAKERNEL, accel=pt.ACCEL_BRUTE)))
+        for name, kw in variants:
             def one(i):
                 p = make_params(pt, wl, first_frame=i, light_p1=light[0], light_ea=light[1], light_eb=light[2], **kw)
                 dev.render(scene, p, frame, None)

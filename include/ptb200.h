@@ -163,6 +163,8 @@ int ptb_render_host(ptb_device* dev, const ptb_triangle* tris, int n_tris, const
  * and returns the totals since the previous read.  kernel_launches counts this
  * library's own kernel launches (always on).                                      */
 int ptb_device_profile(ptb_device* dev, int enable);
+/* experiment knobs for A/B measurements, index 0..7 (results never change) */
+int ptb_device_set_tuning(ptb_device* dev, int index, int value);
 int ptb_device_profile_read(ptb_device* dev, float* integrator_ms, float* resolve_ms, int* integrator_launches,
                             uint64_t* kernel_launches);
 

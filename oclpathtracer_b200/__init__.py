@@ -86,7 +86,7 @@ EXPORTS = [
     "ptb_light_from_quad", "ptb_free", "ptb_to_rgb8", "ptb_write_ppm", "ptb_bvh_params_default",
     "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_copy_bvh",
     "ptb_render_params_default", "ptb_render_local_pixels", "ptb_render", "ptb_render_host", "ptb_trace",
-    "ptb_device_profile", "ptb_device_profile_read", "ptb_test_sincos", "ptb_test_pow", "ptb_test_rng", "ptb_test_camera",
+    "ptb_device_profile", "ptb_device_profile_read", "ptb_device_set_tuning", "ptb_test_sincos", "ptb_test_pow", "ptb_test_rng", "ptb_test_camera",
 ]
 
 
@@ -135,6 +135,7 @@ def lib():
         L.ptb_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 9
         L.ptb_device_profile.argtypes = [C.c_void_p, C.c_int]
         L.ptb_device_profile_read.argtypes = [C.c_void_p] * 5
+        L.ptb_device_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ptb_test_sincos.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptb_test_pow.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]
         L.ptb_test_rng.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
@@ -284,6 +285,9 @@ class Device:
 
     def stream(self):
         return lib().ptb_device_stream(self._h)
+
+    def set_tuning(self, index, value):
+        _check(lib().ptb_device_set_tuning(self._h, index, value))
 
     def profile(self, enable=True):
         _check(lib().ptb_device_profile(self._h, 1 if enable else 0))

@@ -78,27 +78,29 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
                 : "memory");
         }
     }
-    c.s_nodes = s_nodes;
-    c.s_tris = s_tris;
-    c.s_mats = s_mats;
+    c.s_nodes = smem_u32(s_nodes);
+    c.s_tris = smem_u32(s_tris);
+    c.s_mats = smem_u32(s_mats);
     c.g_nodes = sc.nodes;
     c.g_tris = TRIS_BVH ? sc.tris : sc.tris_orig;
     c.g_mats = sc.mats;
-    c.stride = blockDim.x;
-    c.stack_ref = reinterpret_cast<int*>(s_stack) + threadIdx.x;
-    c.stack_tn = reinterpret_cast<float*>(s_stack + (size_t)sc.stack_depth * blockDim.x * 4) + threadIdx.x;
+    c.stride_bytes = blockDim.x * 4u;
+    const uint32_t stack_bytes = NODES ? (uint32_t)sc.stack_depth * blockDim.x * 4u : 0u;
+    c.s_stack_ref = smem_u32(s_stack) + threadIdx.x * 4u;
+    c.s_stack_tn = c.s_stack_ref + stack_bytes;
+    c.s_scratch = c.s_stack_tn + stack_bytes;
     c.smem_nodes = sc.smem_nodes;
     c.n_tris = sc.n_tris;
     return c;
 }
 
 // host helper: bytes of dynamic shared memory for a launch
-static inline size_t scene_smem_bytes(const SceneDev& sc, bool bvh, bool small, int block) {
+static inline size_t scene_smem_bytes(const SceneDev& sc, bool bvh, bool small, int block, size_t scratch_per_thread = 0) {
     size_t b = 16;
     if (bvh) b += (size_t)sc.smem_nodes * 64;
     if (small) b += (size_t)sc.n_tris * 48 + (size_t)sc.n_mats * 32;
     if (bvh) b += (size_t)sc.stack_depth * block * 8;
-    return b;
+    return b + scratch_per_thread * block;
 }
 
 // ---- per-sample integrators ------------------------------------------------------------------
@@ -117,6 +119,7 @@ struct RenderArgs {
     ptb_pixel_stats* stats;     // per local pixel, written for stats_frame only
     int stats_frame;
     unsigned long long* counters;
+    int tune[4];           // experiment knobs (ptb_device_set_tuning); never change results
 };
 
 template <bool STATS>
@@ -308,7 +311,8 @@ __global__ void __launch_bounds__(128) k_mega(const SceneDev sc, const RenderArg
     const long long total = (long long)a.frames_in_batch * a.n_local;
     RayCount rc{0u, 0u};
     QueryStats qs{0u, 0u};
-    if (slot < total) {
+    const bool valid = slot < total;
+    if (valid) {
         const int fi = (int)(slot / a.n_local);
         const int li = (int)(slot - (long long)fi * a.n_local);
         const int gid = gid_of_local(a.shard, li);
@@ -325,13 +329,9 @@ __global__ void __launch_bounds__(128) k_mega(const SceneDev sc, const RenderArg
         a.samples[slot] = make_float4(col.x, col.y, col.z, 1.0f);
         if constexpr (STATS) {
             if (a.stats && frame == a.stats_frame) {
-                ptb_pixel_stats ps;
-                ps.tri = st.tri; ps.quad = st.quad; ps.t_bits = st.t_bits;
-                ps.visits_primary = st.visits_primary; ps.visits_secondary = st.visits_secondary;
-                ps.count = st.count; ps.id_hash = st.id_hash; ps.tri_tests = qs.tests;
                 uint4* dst = reinterpret_cast<uint4*>(a.stats + li);
-                dst[0] = make_uint4((uint32_t)ps.tri, (uint32_t)ps.quad, ps.t_bits, ps.visits_primary);
-                dst[1] = make_uint4(ps.visits_secondary, ps.count, ps.id_hash, ps.tri_tests);
+                dst[0] = make_uint4((uint32_t)st.tri, (uint32_t)st.quad, st.t_bits, st.visits_primary);
+                dst[1] = make_uint4(st.visits_secondary, st.count, st.id_hash, qs.tests);
             }
         }
     }
