@@ -71,6 +71,13 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -83,7 +90,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if not self.proc:
@@ -94,11 +101,14 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        lo = (self.t0 or 0.0) - 0.03
+        hi = (self.t1 or 1e18) + 0.03
+        rows = [r for (ts, r) in self.rows if lo <= ts <= hi] or [r for (_, r) in self.rows[-3:]]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
@@ -270,6 +280,8 @@ def main():
     stat_ctr = dev.render(scene, params(rank, collect_stats=1), frame, None, want_counters=True)
     accum_t.zero_()
 
+    sampler = ClockSampler(local)
+    sampler.start()  # nvidia-smi needs ~100 ms to come up: start it before the warm-up, keep only timed-region rows
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
@@ -279,8 +291,7 @@ def main():
 
     dev.profile(True)
     dev.profile_read()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark_begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
     for i in range(args.steps):
         flush.fill_(i & 255)           # evict L2 between timed iterations (untimed)
@@ -293,6 +304,7 @@ def main():
         dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
     ev[-1][1].record(stream)
     torch.cuda.synchronize()
+    sampler.mark_end()
     clocks = sampler.stop()
     prof = dev.profile_read()
     dev.profile(False)
@@ -315,26 +327,52 @@ def main():
     e2e = None
     if not args.no_e2e:
         dev2 = pt.Device(local)
-        out = np.zeros((npix, 4), np.float32)
-        prm0 = params(rank)
-        for i in range(max(1, args.warmup)):
-            dev2.render_host(tris, mats, prm0, out=out, want_counters=False)
+        # page-locked host buffers: the caller's records (inputs) and two result frames (double buffering)
+        tp, mp = pt.PinnedArray(tris.shape, tris.dtype), pt.PinnedArray(mats.shape, mats.dtype)
+        tp.array[...] = tris
+        mp.array[...] = mats
+        outs = [pt.PinnedArray((npix, 4), np.float32), pt.PinnedArray((npix, 4), np.float32)]
+
+        def e2e_loop(pipelined):
+            rays = 0
+            prev = None
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                job = dev2.render_host_async(tp.array, mp.array, params(i * world + rank), outs[i & 1].array)
+                if not pipelined:
+                    dev2.job_wait(job)
+                else:
+                    if prev is not None:
+                        dev2.job_wait(prev)   # frame i-1 is now in host memory while frame i renders
+                    prev = job
+                rays += rays_per_step[i]
+            if prev is not None:
+                dev2.job_wait(prev)
+            return time.perf_counter() - t0, rays
+
+        for _ in range(2):
+            e2e_loop(True)
         if world > 1:
             dist.barrier()
-        e2e_rays = 0
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            _, _, _ = dev2.render_host(tris, mats, params(i * world + rank), out=out, want_counters=False)
-            e2e_rays += rays_per_step[i]
-        t_e2e = time.perf_counter() - t0
-        te = torch.tensor([t_e2e, float(e2e_rays)], dtype=torch.float64, device="cuda")
+        t_sync, _ = e2e_loop(False)
         if world > 1:
-            a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
-            b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
-            t_e2e, e2e_rays = float(a[0]), float(b[1])
+            dist.barrier()
+        t_e2e, e2e_rays = e2e_loop(True)
+        checksum = float(outs[(args.steps - 1) & 1].array[:, 0].sum())  # the result is really on the host
+        te = torch.tensor([t_e2e, float(e2e_rays), t_sync], dtype=torch.float64, device="cuda")
+        if world > 1:
+            a_ = te.clone(); dist.all_reduce(a_, op=dist.ReduceOp.MAX)
+            b_ = te.clone(); dist.all_reduce(b_, op=dist.ReduceOp.SUM)
+            t_e2e, e2e_rays, t_sync = float(a_[0]), float(b_[1]), float(a_[2])
         e2e = {"value": e2e_rays / t_e2e / 1e6, "unit": "Mrays/s",
-               "h2d_bytes_per_step": int(tris.nbytes + mats.nbytes), "d2h_bytes_per_step": int(out.nbytes),
-               "ms_per_step": t_e2e / args.steps * 1e3, "timing": "host wall clock around ptb_render_host (it synchronises)"}
+               "h2d_bytes_per_step": int(tris.nbytes + mats.nbytes), "d2h_bytes_per_step": int(npix * 16),
+               "ms_per_step": t_e2e / args.steps * 1e3,
+               "synchronous_value": e2e_rays / t_sync / 1e6, "synchronous_ms_per_step": t_sync / args.steps * 1e3,
+               "host_checksum": checksum,
+               "timing": "host wall clock over K x {ptb_render_host_async (H2D records, render, D2H float4 frame into pinned host memory), "
+                         "ptb_job_wait of the previous step}: D2H of step i overlaps the render of step i+1; synchronous_* waits every step"}
+        for pa in (tp, mp, *outs):
+            pa.free()
         dev2.close()
 
     # ---- roofline of the dominant kernel (the integrator launch) --------------------------------------------
@@ -349,8 +387,12 @@ def main():
     achieved_gbs = bytes_per_ray * rays_per_launch / (integ_ms * 1e-3) / 1e9
     sm_count = dev.sm_count()
     # fp32 lane-op estimate per ray: slab 24 per box, 2 boxes per node; MT stages from the oracle's exact stage counts
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+        traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
     roof = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-            "traffic": None, "peak_source": peak_src, "kernel": "k_mega<AO>" if wl["mode"] == 1 else "integrator",
+            "traffic": traffic, "peak_source": peak_src, "kernel": "k_mega<AO>" if wl["mode"] == 1 else "integrator",
             "kernel_ms": integ_ms, "kernel_share_of_step": prof["integrator_ms"] / ms_steps if ms_steps else None,
             "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tri_tests_per_ray": tests_per_ray,
             "note": "algorithmic bytes = nodes*64 + tri_tests*48 + 16 B/sample (SURVEY 8d); the 5 KB scene is shared-memory resident, so this "

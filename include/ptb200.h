@@ -156,6 +156,18 @@ int ptb_render_host(ptb_device* dev, const ptb_triangle* tris, int n_tris, const
                     const ptb_render_params* params, float* out_rgba, ptb_pixel_stats* out_stats,
                     ptb_counters* counters);
 
+/* Pipelined form: _async enqueues H2D + render + D2H and returns; ptb_job_wait blocks until that job's
+ * frame (and stats) are in the caller's buffers and releases the job.  At most two jobs may be in flight
+ * (double buffering: job j's D2H overlaps job j+1's render).  Buffers from ptb_host_alloc are pinned, so the
+ * copies go straight to / from them; pageable buffers are staged.  Counters are not available here.      */
+typedef struct ptb_job ptb_job;
+int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats, int n_mats,
+                          const ptb_render_params* params, float* out_rgba, ptb_pixel_stats* out_stats,
+                          ptb_job** job);
+int ptb_job_wait(ptb_job* job);
+int ptb_host_alloc(size_t bytes, void** out); /* page-locked host memory */
+int ptb_host_free(void* p);
+
 /* ---- measurement hooks ----------------------------------------------------------------
  * (the reference's analogue: Device::toggleProfiling + the ms launch1D returns,
  * Adl/Adl.h:143-171, Adl/CL/AdlKernelUtilsCL.cpp:470-499).  With profiling on, every

@@ -85,7 +85,8 @@ EXPORTS = [
     "ptb_kernel_get", "ptb_kernel_set_int", "ptb_launch1d", "ptb_load_model", "ptb_tessellate",
     "ptb_light_from_quad", "ptb_free", "ptb_to_rgb8", "ptb_write_ppm", "ptb_bvh_params_default",
     "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_copy_bvh",
-    "ptb_render_params_default", "ptb_render_local_pixels", "ptb_render", "ptb_render_host", "ptb_trace",
+    "ptb_render_params_default", "ptb_render_local_pixels", "ptb_render", "ptb_render_host",
+    "ptb_render_host_async", "ptb_job_wait", "ptb_host_alloc", "ptb_host_free", "ptb_trace",
     "ptb_device_profile", "ptb_device_profile_read", "ptb_device_set_tuning", "ptb_test_sincos", "ptb_test_pow", "ptb_test_rng", "ptb_test_camera",
 ]
 
@@ -129,6 +130,11 @@ def lib():
         L.ptb_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ptb_render_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ptb_render_host_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ptb_job_wait.argtypes = [C.c_void_p]
+        L.ptb_host_alloc.argtypes = [C.c_size_t, C.c_void_p]
+        L.ptb_host_free.argtypes = [C.c_void_p]
         L.ptb_kernel_get.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p]
         L.ptb_kernel_set_int.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.ptb_launch1d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
@@ -334,6 +340,16 @@ class Device:
                                      _p(stats), C.byref(ctr) if ctr is not None else None))
         return out, stats, (ctr.as_dict() if ctr is not None else None)
 
+    def render_host_async(self, tris, mats, params, out, stats=None):
+        """Returns a job handle; call job_wait(handle) before reading `out`.  At most two in flight."""
+        job = C.c_void_p()
+        _check(lib().ptb_render_host_async(self._h, _p(tris), len(tris), _p(mats), len(mats), C.byref(params), _p(out),
+                                           _p(stats), C.byref(job)))
+        return job
+
+    def job_wait(self, job):
+        _check(lib().ptb_job_wait(job))
+
     def kernel(self, file_name, func_name):
         k = C.c_void_p()
         _check(lib().ptb_kernel_get(self._h, file_name.encode(), func_name.encode(), C.byref(k)))
@@ -457,6 +473,24 @@ class Scene:
             self._h = C.c_void_p()
             if self in self.dev._children:
                 self.dev._children.remove(self)
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory (ptb_host_alloc); free() when done."""
+
+    def __init__(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        self._p = C.c_void_p()
+        _check(lib().ptb_host_alloc(n, C.byref(self._p)))
+        buf = (C.c_uint8 * n).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().ptb_host_free(self._p)
+            self._p = C.c_void_p()
 
 
 def bvh_params(**kw):

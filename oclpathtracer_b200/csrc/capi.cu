@@ -54,8 +54,18 @@ struct ptb_device {
     // ptb_render_host cache
     ptb_scene* host_scene = nullptr; uint64_t host_scene_hash = 0;
     ptb_buffer* host_tris = nullptr; ptb_buffer* host_mats = nullptr;
-    ptb_buffer* host_frame = nullptr; ptb_buffer* host_stats = nullptr;
-    void* pinned = nullptr; size_t pinned_bytes = 0;
+    void* pinned = nullptr; size_t pinned_bytes = 0;  // staging of the scene records
+    cudaStream_t copy_stream = nullptr;               // D2H of finished frames overlaps the next render
+    struct HostSlot {
+        ptb_buffer* frame = nullptr; ptb_buffer* stats = nullptr;
+        void* pin = nullptr; size_t pin_bytes = 0;    // staging when the caller's buffers are pageable
+        cudaEvent_t ev_render = nullptr, ev_done = nullptr;
+        bool busy = false;
+        float* out = nullptr; ptb_pixel_stats* out_stats = nullptr;
+        size_t fb = 0, sb = 0;
+        bool direct_frame = false, direct_stats = false;
+    } slots[2];
+    uint64_t jobs_submitted = 0;
     int tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // experiment knobs (ptb_device_set_tuning)
     // measurement
     bool profiling = false;
@@ -183,7 +193,15 @@ extern "C" int ptb_device_destroy(ptb_device* dev) {
     set_device(dev);
     cudaStreamSynchronize(dev->stream);
     if (dev->host_scene) ptb_scene_destroy(dev->host_scene);
-    for (ptb_buffer* b : {dev->host_tris, dev->host_mats, dev->host_frame, dev->host_stats})
+    for (auto& sl : dev->slots) {
+        if (sl.frame) ptb_buffer_destroy(sl.frame);
+        if (sl.stats) ptb_buffer_destroy(sl.stats);
+        if (sl.pin) cudaFreeHost(sl.pin);
+        if (sl.ev_render) cudaEventDestroy(sl.ev_render);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
+    if (dev->copy_stream) cudaStreamDestroy(dev->copy_stream);
+    for (ptb_buffer* b : {dev->host_tris, dev->host_mats})
         if (b) ptb_buffer_destroy(b);
     for (auto& kv : dev->kernels) {
         if (kv.second->scene) ptb_scene_destroy(kv.second->scene);
@@ -605,9 +623,17 @@ extern "C" int ptb_render(ptb_device* dev, ptb_scene* scene, const ptb_render_pa
                        stats ? static_cast<ptb_pixel_stats*>(stats->d_ptr) : nullptr, stats ? stats->bytes : 0, counters);
 }
 
+// content hash of the caller's records (decides whether the resident scene must be rebuilt)
 static uint64_t fnv1a(const void* p, size_t n, uint64_t h) {
     const unsigned char* b = static_cast<const unsigned char*>(p);
-    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {  // word-wise: the 2M-triangle scene is 128 MB
+        uint64_t w;
+        std::memcpy(&w, b + i, 8);
+        h = (h ^ w) * 1099511628211ull;
+        h ^= h >> 29;
+    }
+    for (; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
     return h;
 }
 
@@ -618,53 +644,154 @@ static int ensure_buffer(ptb_device* dev, ptb_buffer** b, size_t bytes) {
     return ptb_buffer_create(dev, bytes, b);
 }
 
-extern "C" int ptb_render_host(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats,
-                               int n_mats, const ptb_render_params* params, float* out_rgba,
-                               ptb_pixel_stats* out_stats, ptb_counters* counters) {
-    if (!dev || !tris || !mats || !out_rgba) return fail(PTB_E_INVALID, "ptb_render_host: null argument");
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+extern "C" int ptb_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(PTB_E_INVALID, "ptb_host_alloc: null out");
+    *out = nullptr;
+    CU_TRY(cudaMallocHost(out, bytes ? bytes : 1));
+    return PTB_OK;
+}
+extern "C" int ptb_host_free(void* p) {
+    if (p) CU_TRY(cudaFreeHost(p));
+    return PTB_OK;
+}
+
+struct ptb_job {
+    ptb_device* dev;
+    int slot;
+    uint64_t serial;
+};
+
+extern "C" int ptb_job_wait(ptb_job* job) {
+    if (!job) return fail(PTB_E_INVALID, "ptb_job_wait: null job");
+    ptb_device* dev = job->dev;
+    auto& sl = dev->slots[job->slot];
+    int rc = PTB_OK;
+    if (sl.busy) {
+        if (set_device(dev)) rc = PTB_E_CUDA;
+        cudaError_t e = cudaEventSynchronize(sl.ev_done);
+        if (e != cudaSuccess) rc = fail(PTB_E_CUDA, "ptb_job_wait: %s", cudaGetErrorString(e));
+        if (rc == PTB_OK) {
+            char* pin = static_cast<char*>(sl.pin);
+            if (!sl.direct_frame) std::memcpy(sl.out, pin, sl.fb);
+            if (sl.sb && !sl.direct_stats) std::memcpy(sl.out_stats, pin + sl.fb, sl.sb);
+        }
+        sl.busy = false;
+    }
+    delete job;
+    return rc;
+}
+
+// Asynchronous end-to-end render with HOST buffers.  Two slots are double-buffered: while the
+// frame of job j travels device->host on the copy stream, job j+1 renders on the main stream.
+extern "C" int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats,
+                                     int n_mats, const ptb_render_params* params, float* out_rgba,
+                                     ptb_pixel_stats* out_stats, ptb_job** job_out) {
+    if (!dev || !tris || !mats || !out_rgba || !job_out) return fail(PTB_E_INVALID, "ptb_render_host_async: null argument");
+    *job_out = nullptr;
     if (int rc = validate(params)) return rc;
     if (set_device(dev)) return PTB_E_CUDA;
     const int n_local = ptb_render_local_pixels(params);
     const size_t tb = size_t(n_tris) * sizeof(ptb_triangle), mb = size_t(n_mats) * sizeof(ptb_material);
     const size_t fb = size_t(n_local) * 16, sb = out_stats ? size_t(n_local) * sizeof(ptb_pixel_stats) : 0;
-    // 1. H2D: the caller's records, as the reference flow uploads tBuffer / materialBuffer (RaytraceTest.cpp:222-246)
+    const int si = int(dev->jobs_submitted & 1);
+    auto& sl = dev->slots[si];
+    if (sl.busy) return fail(PTB_E_INVALID, "ptb_render_host_async: more than two jobs in flight; wait for the older one first");
     int rc;
-    if ((rc = ensure_buffer(dev, &dev->host_tris, tb)) || (rc = ensure_buffer(dev, &dev->host_mats, mb)) ||
-        (rc = ensure_buffer(dev, &dev->host_frame, fb)) || (sb && (rc = ensure_buffer(dev, &dev->host_stats, sb))))
-        return rc;
-    if (dev->pinned_bytes < tb + mb + fb + sb) {
-        if (dev->pinned) cudaFreeHost(dev->pinned);
-        dev->pinned = nullptr; dev->pinned_bytes = 0;
-        CU_TRY(cudaMallocHost(&dev->pinned, tb + mb + fb + sb));
-        dev->pinned_bytes = tb + mb + fb + sb;
+    if (!dev->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
+    if (!sl.ev_render) {
+        CU_TRY(cudaEventCreateWithFlags(&sl.ev_render, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
     }
-    char* pin = static_cast<char*>(dev->pinned);
-    std::memcpy(pin, tris, tb);
-    std::memcpy(pin + tb, mats, mb);
-    if ((rc = ptb_buffer_write(dev->host_tris, pin, tb, 0)) || (rc = ptb_buffer_write(dev->host_mats, pin + tb, mb, 0))) return rc;
+    // 1. H2D of the caller's records, as the reference flow uploads tBuffer / materialBuffer (RaytraceTest.cpp:222-246)
+    if ((rc = ensure_buffer(dev, &dev->host_tris, tb)) || (rc = ensure_buffer(dev, &dev->host_mats, mb)) ||
+        (rc = ensure_buffer(dev, &sl.frame, fb)) || (sb && (rc = ensure_buffer(dev, &sl.stats, sb))))
+        return rc;
     // 2. resident scene (BVH + relaid records) is rebuilt only when the records changed
     uint64_t h = fnv1a(tris, tb, 1469598103934665603ull);
     h = fnv1a(mats, mb, h);
-    if (!dev->host_scene || dev->host_scene_hash != h) {
+    const bool scene_changed = !dev->host_scene || dev->host_scene_hash != h;
+    const void* src_t = tris;
+    const void* src_m = mats;
+    if (!is_pinned(tris) || !is_pinned(mats)) {  // pageable records go through pinned staging
+        if (dev->pinned_bytes < tb + mb) {
+            CU_TRY(cudaStreamSynchronize(dev->stream));
+            if (dev->pinned) cudaFreeHost(dev->pinned);
+            dev->pinned = nullptr; dev->pinned_bytes = 0;
+            CU_TRY(cudaMallocHost(&dev->pinned, tb + mb));
+            dev->pinned_bytes = tb + mb;
+        } else {
+            CU_TRY(cudaStreamSynchronize(dev->stream));  // the previous upload must have left the staging area
+        }
+        std::memcpy(dev->pinned, tris, tb);
+        std::memcpy(static_cast<char*>(dev->pinned) + tb, mats, mb);
+        src_t = dev->pinned;
+        src_m = static_cast<char*>(dev->pinned) + tb;
+    }
+    if ((rc = ptb_buffer_write(dev->host_tris, src_t, tb, 0)) || (rc = ptb_buffer_write(dev->host_mats, src_m, mb, 0))) return rc;
+    if (scene_changed) {
         if (dev->host_scene) ptb_scene_destroy(dev->host_scene);
         dev->host_scene = nullptr;
         if ((rc = ptb_scene_create(dev, tris, n_tris, mats, n_mats, nullptr, &dev->host_scene))) return rc;
         dev->host_scene_hash = h;
     }
-    // 3. in/out frame state for the reference accumulation
-    if (params->accum == PTB_ACCUM_REFERENCE && params->first_frame > 0) {
-        std::memcpy(pin + tb + mb, out_rgba, fb);
-        if ((rc = ptb_buffer_write(dev->host_frame, pin + tb + mb, fb, 0))) return rc;
+    // 3. output staging
+    sl.direct_frame = is_pinned(out_rgba);
+    sl.direct_stats = sb ? is_pinned(out_stats) : true;
+    const size_t need_pin = (sl.direct_frame ? 0 : fb) + (sl.direct_stats ? 0 : sb);
+    if (need_pin && sl.pin_bytes < fb + sb) {
+        if (sl.pin) cudaFreeHost(sl.pin);
+        sl.pin = nullptr; sl.pin_bytes = 0;
+        CU_TRY(cudaMallocHost(&sl.pin, fb + sb));
+        sl.pin_bytes = fb + sb;
     }
-    // 4. render, 5. D2H
-    if ((rc = render_impl(dev, dev->host_scene, params, static_cast<float4*>(dev->host_frame->d_ptr), dev->host_frame->bytes,
-                          sb ? static_cast<ptb_pixel_stats*>(dev->host_stats->d_ptr) : nullptr, sb ? dev->host_stats->bytes : 0, counters)))
+    // the slot's device frame may still be read by an older copy
+    CU_TRY(cudaStreamWaitEvent(dev->stream, sl.ev_done, 0));
+    if (params->accum == PTB_ACCUM_REFERENCE && params->first_frame > 0)  // in/out state of the gamma-space mean
+        if ((rc = ptb_buffer_write(sl.frame, out_rgba, fb, 0))) return rc;
+    // 4. render on the main stream
+    if ((rc = render_impl(dev, dev->host_scene, params, static_cast<float4*>(sl.frame->d_ptr), sl.frame->bytes,
+                          sb ? static_cast<ptb_pixel_stats*>(sl.stats->d_ptr) : nullptr, sb ? sl.stats->bytes : 0, nullptr)))
         return rc;
-    if ((rc = ptb_buffer_read(dev->host_frame, pin + tb + mb, fb, 0))) return rc;
-    if (sb && (rc = ptb_buffer_read(dev->host_stats, pin + tb + mb + fb, sb, 0))) return rc;
-    CU_TRY(cudaStreamSynchronize(dev->stream));
-    std::memcpy(out_rgba, pin + tb + mb, fb);
-    if (sb) std::memcpy(out_stats, pin + tb + mb + fb, sb);
+    CU_TRY(cudaEventRecord(sl.ev_render, dev->stream));
+    // 5. D2H on the copy stream
+    CU_TRY(cudaStreamWaitEvent(dev->copy_stream, sl.ev_render, 0));
+    char* pin = static_cast<char*>(sl.pin);
+    CU_TRY(cudaMemcpyAsync(sl.direct_frame ? (void*)out_rgba : (void*)pin, sl.frame->d_ptr, fb, cudaMemcpyDeviceToHost, dev->copy_stream));
+    if (sb) CU_TRY(cudaMemcpyAsync(sl.direct_stats ? (void*)out_stats : (void*)(pin + fb), sl.stats->d_ptr, sb, cudaMemcpyDeviceToHost, dev->copy_stream));
+    CU_TRY(cudaEventRecord(sl.ev_done, dev->copy_stream));
+    sl.busy = true; sl.out = out_rgba; sl.out_stats = out_stats; sl.fb = fb; sl.sb = sb;
+    ptb_job* job = new ptb_job{dev, si, dev->jobs_submitted};
+    dev->jobs_submitted++;
+    *job_out = job;
+    return PTB_OK;
+}
+
+extern "C" int ptb_render_host(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats,
+                               int n_mats, const ptb_render_params* params, float* out_rgba,
+                               ptb_pixel_stats* out_stats, ptb_counters* counters) {
+    if (!dev) return fail(PTB_E_INVALID, "ptb_render_host: null argument");
+    for (auto& sl : dev->slots)
+        if (sl.busy) return fail(PTB_E_INVALID, "ptb_render_host: asynchronous jobs are still in flight");
+    ptb_job* job = nullptr;
+    int rc = ptb_render_host_async(dev, tris, n_tris, mats, n_mats, params, out_rgba, out_stats, &job);
+    if (rc) return rc;
+    rc = ptb_job_wait(job);
+    if (rc) return rc;
+    if (counters) {
+        unsigned long long hc[ptd::CTR_COUNT];
+        CU_TRY(cudaMemcpyAsync(hc, dev->counters, sizeof hc, cudaMemcpyDeviceToHost, dev->stream));
+        CU_TRY(cudaStreamSynchronize(dev->stream));
+        std::memset(counters, 0, sizeof *counters);
+        counters->rays_closest = hc[ptd::CTR_CLOSEST]; counters->rays_any = hc[ptd::CTR_ANY];
+        counters->nodes = hc[ptd::CTR_NODES]; counters->tri_tests = hc[ptd::CTR_TESTS];
+        counters->samples = (uint64_t)ptb_render_local_pixels(params) * (uint64_t)params->n_frames;
+    }
     return PTB_OK;
 }
 

@@ -386,3 +386,37 @@ def test_cpp_raycast_flow_matches_oracle(ob, cornell, tmp_path):
     tris, mats = cornell
     want, _, _ = ob.render(ob.default_params(64, 64, first_frame=0, n_frames=5, mode=3, accum=ob.ACCUM_REFERENCE), tris, mats)
     assert vals == ob.to_rgb8(want).reshape(-1).tolist()
+
+
+def test_async_host_pipeline(dev, pt, cornell):
+    """ptb_render_host_async / ptb_job_wait: double-buffered jobs return exactly the synchronous results."""
+    tris, mats = cornell
+    w, h, n = 160, 96, 6
+    want = [dev.render_host(tris, mats, pt.default_params(width=w, height=h, first_frame=f, n_frames=1, mode=pt.MODE_AO,
+                                                          accum=pt.ACCUM_LINEAR), want_counters=False)[0].copy() for f in range(n)]
+    pinned = [pt.PinnedArray((w * h, 4), np.float32) for _ in range(2)]
+    pageable = [np.zeros((w * h, 4), np.float32) for _ in range(2)]
+    for bufs in ([p.array for p in pinned], pageable):
+        prev, got = None, []
+        for f in range(n):
+            prm = pt.default_params(width=w, height=h, first_frame=f, n_frames=1, mode=pt.MODE_AO, accum=pt.ACCUM_LINEAR)
+            job = dev.render_host_async(tris, mats, prm, bufs[f & 1])
+            if prev is not None:
+                dev.job_wait(prev[0])
+                got.append(bufs[prev[1] & 1].copy())
+            prev = (job, f)
+        dev.job_wait(prev[0])
+        got.append(bufs[prev[1] & 1].copy())
+        for f in range(n):
+            assert got[f].tobytes() == want[f].tobytes(), f
+    # a third job in flight is refused, and the synchronous call refuses to run under in-flight jobs
+    prm = pt.default_params(width=w, height=h, mode=pt.MODE_AO, accum=pt.ACCUM_LINEAR)
+    j1 = dev.render_host_async(tris, mats, prm, pageable[0])
+    j2 = dev.render_host_async(tris, mats, prm, pageable[1])
+    with pytest.raises(pt.PtbError, match="two jobs"):
+        dev.render_host_async(tris, mats, prm, pinned[0].array)
+    with pytest.raises(pt.PtbError, match="in flight"):
+        dev.render_host(tris, mats, prm)
+    dev.job_wait(j1); dev.job_wait(j2)
+    for p in pinned:
+        p.free()
