@@ -441,6 +441,23 @@ static int set_smem(K kernel, size_t smem) {
 template <int MODE, bool BVH, bool SMALL, bool STATS>
 static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::RenderArgs& a) {
     const int block = (a.tune[3] == 64 || a.tune[3] == 32) ? a.tune[3] : 128;
+    if (MODE == PTB_MODE_PATH && a.tune[5] == 0) {  // persistent grid with path regeneration (tune[5]=1: one sample per thread)
+        const size_t smem = ptd::scene_smem_bytes(sc, BVH, SMALL, block);
+        auto k = ptd::k_mega_path_regen<BVH, SMALL, STATS>;
+        if (int rc = set_smem(k, smem)) return rc;
+        int per_sm = 0;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, block, smem));
+        if (per_sm < 1) per_sm = 1;
+        const long long total = (long long)a.frames_in_batch * a.n_local;
+        long long grid = (long long)per_sm * dev->prop.multiProcessorCount;
+        const long long need = (total + block - 1) / block;
+        if (grid > need) grid = need;
+        unsigned long long* work = dev->counters + 32;
+        CU_TRY(cudaMemsetAsync(work, 0, sizeof(unsigned long long), dev->stream));
+        k<<<(unsigned)grid, block, smem, dev->stream>>>(sc, a, work);
+        CU_TRY(cudaGetLastError());
+        return PTB_OK;
+    }
     const long long total = (long long)a.frames_in_batch * a.n_local;
     const unsigned grid = (unsigned)((total + block - 1) / block);
     const size_t smem = ptd::scene_smem_bytes(sc, BVH, SMALL, block);
@@ -562,7 +579,7 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
     a.stats = stats ? d_stats : nullptr;
     a.stats_frame = p->first_frame + p->n_frames - 1;
     a.counters = dev->counters;
-    for (int k = 0; k < 4; ++k) a.tune[k] = dev->tune[k];
+    for (int k = 0; k < 8; ++k) a.tune[k] = dev->tune[k];
 
     int integrator = p->integrator;
     if (integrator == PTB_INTEGRATOR_AUTO) integrator = PTB_INTEGRATOR_MEGAKERNEL;

@@ -119,7 +119,7 @@ struct RenderArgs {
     ptb_pixel_stats* stats;     // per local pixel, written for stats_frame only
     int stats_frame;
     unsigned long long* counters;
-    int tune[4];           // experiment knobs (ptb_device_set_tuning); never change results
+    int tune[8];           // experiment knobs (ptb_device_set_tuning); never change results
 };
 
 template <bool STATS>
@@ -151,45 +151,53 @@ struct RayCount {
     uint32_t closest, any;
 };
 
+// One iteration of the path loop, GenerateColors.cl:229-258.  Returns true when the path goes on
+// (r, mask, seed updated), false when it ended; radiance accumulates either way.
+template <bool BVH, bool SMALL, bool STATS>
+PTD_FI bool path_segment(const Ctx& c, Ray& r, uint32_t& seed, V3& radiance, V3& mask, int i, int max_depth,
+                         SampleStats<STATS>& st, RayCount& rc, QueryStats& qs) {
+    Hit h;
+    const uint32_t v0 = qs.visits;
+    const bool hit = q_closest<BVH, SMALL, STATS>(c, r.o, r.d, h, qs);
+    rc.closest++;
+    V3 p1, e1, e2; int idx = -1, quad = -1;
+    if (hit) load_tri<SMALL>(c, h.pos, p1, e1, e2, idx, quad);
+    if constexpr (STATS) {
+        if (i == 0) st_primary(st, hit, h, quad, qs.visits - v0);
+        else st_secondary(st, hit ? h.idx : -1, qs.visits - v0);
+        st.count++;
+    }
+    if (!hit) {  // :233-237, max(bg, 0) = bg
+        radiance = mk(radiance.x + mask.x * 0.45f, radiance.y + mask.y * 0.45f, radiance.z + mask.z * 0.45f);
+        return false;
+    }
+    V3 p, n;
+    hit_point_normal(e1, e2, r.o, r.d, h, p, n);
+    V3 albedo, emissive; float roughness; int type;
+    load_mat<SMALL>(c, quad, albedo, roughness, emissive, type);  // :239
+    radiance = mk(radiance.x + mask.x * emissive.x * 3.0f, radiance.y + mask.y * emissive.y * 3.0f,
+                  radiance.z + mask.z * emissive.z * 3.0f);      // :241
+    if (i + 1 >= max_depth) return false;  // the last segment's BSDF sample cannot reach the radiance
+    n = dot(n, r.d) < 0.0f ? n : mul(n, -1.0f);                   // :243
+    V3 wi = mk(0.0f, 0.0f, 0.0f);
+    const V3 wo = neg(r.d);                                       // :246
+    float pdf = 0.0f;                                             // :247
+    const V3 color = brdf(wo, wi, pdf, n, albedo, roughness, type, seed);  // :249
+    if (pdf <= 0.0f) return false;                                // :251
+    const float dw = dot(wi, n);
+    mask = mk(mask.x * (color.x * dw / pdf), mask.y * (color.y * dw / pdf), mask.z * (color.z * dw / pdf));  // :253-255
+    r = get_ray(add(p, mul(wi, 0.01f)), wi);                      // :257
+    return true;
+}
+
 // GenerateColors.cl:223-261 with BOUNCES -> max_depth
 template <bool BVH, bool SMALL, bool STATS>
 PTD_FI V3 trace_rays(const Ctx& c, Ray r, uint32_t& seed, int max_depth, SampleStats<STATS>& st, RayCount& rc,
                      QueryStats& qs) {
     V3 radiance = mk(0.0f, 0.0f, 0.0f);  // :225
     V3 mask = mk(1.0f, 1.0f, 1.0f);      // :226
-    for (int i = 0; i < max_depth; ++i) {  // :229
-        Hit h;
-        const uint32_t v0 = qs.visits;
-        const bool hit = q_closest<BVH, SMALL, STATS>(c, r.o, r.d, h, qs);
-        rc.closest++;
-        V3 p1, e1, e2; int idx = -1, quad = -1;
-        if (hit) load_tri<SMALL>(c, h.pos, p1, e1, e2, idx, quad);
-        if constexpr (STATS) {
-            if (i == 0) st_primary(st, hit, h, quad, qs.visits - v0);
-            else st_secondary(st, hit ? h.idx : -1, qs.visits - v0);
-            st.count++;
-        }
-        if (!hit) {  // :233-237, max(bg, 0) = bg
-            radiance = mk(radiance.x + mask.x * 0.45f, radiance.y + mask.y * 0.45f, radiance.z + mask.z * 0.45f);
-            break;
-        }
-        V3 p, n;
-        hit_point_normal(e1, e2, r.o, r.d, h, p, n);
-        V3 albedo, emissive; float roughness; int type;
-        load_mat<SMALL>(c, quad, albedo, roughness, emissive, type);  // :239
-        radiance = mk(radiance.x + mask.x * emissive.x * 3.0f, radiance.y + mask.y * emissive.y * 3.0f,
-                      radiance.z + mask.z * emissive.z * 3.0f);      // :241
-        if (i + 1 == max_depth) break;  // the last segment's BSDF sample cannot reach the radiance
-        n = dot(n, r.d) < 0.0f ? n : mul(n, -1.0f);                   // :243
-        V3 wi = mk(0.0f, 0.0f, 0.0f);
-        const V3 wo = neg(r.d);                                       // :246
-        float pdf = 0.0f;                                             // :247
-        const V3 color = brdf(wo, wi, pdf, n, albedo, roughness, type, seed);  // :249
-        if (pdf <= 0.0f) break;                                       // :251
-        const float dw = dot(wi, n);
-        mask = mk(mask.x * (color.x * dw / pdf), mask.y * (color.y * dw / pdf), mask.z * (color.z * dw / pdf));  // :253-255
-        r = get_ray(add(p, mul(wi, 0.01f)), wi);                      // :257
-    }
+    for (int i = 0; i < max_depth; ++i)  // :229
+        if (!path_segment<BVH, SMALL, STATS>(c, r, seed, radiance, mask, i, max_depth, st, rc, qs)) break;
     return mk(cl_max(radiance.x, 0.0f), cl_max(radiance.y, 0.0f), cl_max(radiance.z, 0.0f));  // :260
 }
 
@@ -337,6 +345,79 @@ __global__ void __launch_bounds__(128) k_mega(const SceneDev sc, const RenderArg
     }
     flush_counter(a.counters, CTR_CLOSEST, rc.closest);
     flush_counter(a.counters, CTR_ANY, rc.any);
+    if (STATS) {
+        flush_counter(a.counters, CTR_NODES, qs.visits);
+        flush_counter(a.counters, CTR_TESTS, qs.tests);
+    }
+}
+
+// ---- path megakernel with path regeneration ---------------------------------------------------------
+// Paths end at different depths (miss through the open front, pdf <= 0, depth limit); with one sample per
+// thread a warp idles its finished lanes until its longest path ends (Cornell, depth 8: 3.6 of 8 segments
+// on average).  Here the grid is persistent and a lane whose path ended immediately draws the next sample
+// slot from a global counter (one warp-aggregated atomicAdd per refill), so every warp iteration is one
+// path segment for (nearly) 32 live lanes.  Per-sample arithmetic is unchanged -> identical results.
+template <bool BVH, bool SMALL, bool STATS>
+__global__ void __launch_bounds__(128) k_mega_path_regen(const SceneDev sc, const RenderArgs a,
+                                                         unsigned long long* work_counter) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    const long long total = (long long)a.frames_in_batch * a.n_local;
+    const unsigned lane = threadIdx.x & 31u;
+    RayCount rc{0u, 0u};
+    QueryStats qs{0u, 0u};
+    bool alive = false, done = false;
+    long long slot = 0;
+    int li = 0, frame = 0, depth = 0;
+    uint32_t seed = 0, tests0 = 0;
+    Ray r{mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 1.f)};
+    V3 radiance = mk(0.f, 0.f, 0.f), mask = mk(1.f, 1.f, 1.f);
+    SampleStats<STATS> st{};
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !alive && !done);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!alive && !done) {
+                slot = (long long)base + __popc(need & ((1u << lane) - 1u));
+                if (slot >= total) {
+                    done = true;
+                } else {
+                    const int fi = (int)(slot / a.n_local);
+                    li = (int)(slot - (long long)fi * a.n_local);
+                    const int gid = gid_of_local(a.shard, li);
+                    frame = a.first_frame + fi;
+                    seed = (uint32_t)gid + hash_uint32((uint32_t)frame);                    // GenerateColors.cl:308
+                    r = generate_ray(gid % a.width, gid / a.width, a.width, a.height, seed);  // :310
+                    radiance = mk(0.f, 0.f, 0.f);
+                    mask = mk(1.f, 1.f, 1.f);
+                    depth = 0;
+                    alive = true;
+                    st = SampleStats<STATS>{};
+                    tests0 = qs.tests;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+        if (alive) {
+            const bool more = path_segment<BVH, SMALL, STATS>(c, r, seed, radiance, mask, depth, a.max_depth, st, rc, qs);
+            ++depth;
+            if (!more || depth >= a.max_depth) {
+                a.samples[slot] = make_float4(cl_max(radiance.x, 0.0f), cl_max(radiance.y, 0.0f), cl_max(radiance.z, 0.0f), 1.0f);  // :260
+                if constexpr (STATS) {
+                    if (a.stats && frame == a.stats_frame) {
+                        uint4* dst = reinterpret_cast<uint4*>(a.stats + li);
+                        dst[0] = make_uint4((uint32_t)st.tri, (uint32_t)st.quad, st.t_bits, st.visits_primary);
+                        dst[1] = make_uint4(st.visits_secondary, st.count, st.id_hash, qs.tests - tests0);
+                    }
+                }
+                alive = false;
+            }
+        }
+    }
+    flush_counter(a.counters, CTR_CLOSEST, rc.closest);
     if (STATS) {
         flush_counter(a.counters, CTR_NODES, qs.visits);
         flush_counter(a.counters, CTR_TESTS, qs.tests);

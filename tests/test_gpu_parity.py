@@ -420,3 +420,20 @@ def test_async_host_pipeline(dev, pt, cornell):
     dev.job_wait(j1); dev.job_wait(j2)
     for p in pinned:
         p.free()
+
+
+def test_path_regeneration_equals_one_sample_per_thread(dev, pt, scene):
+    """tune[5]: persistent path megakernel with regeneration (default) vs the plain one-sample-per-thread form."""
+    kw = dict(width=333, height=77, n_frames=3, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR, max_depth=9, collect_stats=1,
+              integrator=pt.INTEGRATOR_MEGAKERNEL, frames_per_batch=2)
+    res = []
+    try:
+        for variant in (0, 1):
+            dev.set_tuning(5, variant)
+            frame, stats = dev.buffer(333 * 77 * 16), dev.buffer(333 * 77 * 32)
+            ctr = dev.render(scene, pt.default_params(**kw), frame, stats, want_counters=True)
+            res.append((frame.read(np.uint32).tobytes(), stats.read(np.uint32).tobytes(), tuple(sorted(ctr.items()))))
+            frame.close(); stats.close()
+    finally:
+        dev.set_tuning(5, 0)
+    assert res[0] == res[1]
