@@ -38,6 +38,7 @@ struct WfBuffers {
     uint32_t* sq_tests;      // STATS
     ptb_pixel_stats* slot_stats;  // STATS: per slot
     unsigned int* counts;    // queue lengths: counts[d] = rays entering depth d
+    unsigned int* work;      // persistent kernels: next ray index, one counter per launch
 };
 
 PTD_FI bool finite3(V3 v) {
@@ -106,6 +107,213 @@ __global__ void __launch_bounds__(128) wf_extend(const SceneDev sc, const WfBuff
     if (STATS) {
         flush_counter(counters, CTR_NODES, qs.visits);
         flush_counter(counters, CTR_TESTS, qs.tests);
+    }
+}
+
+// ---- persistent while-while traversal with dynamic ray fetch ---------------------------------------
+// One warp keeps 32 traversal states.  A lane whose ray ended becomes idle; when a warp vote finds at
+// least `refill_thr` idle lanes (or none traversing) the idle lanes draw fresh ray indices from a global
+// work counter with ONE warp-aggregated atomicAdd and re-arm.  Between refills the classic while-while
+// runs: internal nodes until no lane has one, then the leaves.  Per-ray traversal (order, visit counts,
+// results) is exactly bvh_query's; only which lanes run together changes.
+//   IO::load(i, o, d, tmax) -> false for a hole;  IO::store(i, hit, h, qs) publishes one ray's result.
+template <bool ANY, bool SMALL, bool STATS, class IO>
+PTD_FI void trace_persistent(const Ctx& c, IO& io, const unsigned int n_rays, unsigned int* work_counter,
+                             const int refill_thr, uint32_t& n_traced, QueryStats& total) {
+    const unsigned lane = threadIdx.x & 31u;
+    bool active = false;
+    bool exhausted = false;  // warp-uniform
+    unsigned int idx = 0;
+    V3 o = mk(0.f, 0.f, 0.f), d = o, invd = o, ood = o;
+    float best_t = 0.f, best_u = 0.f, best_v = 0.f;
+    int best_pos = -1, best_idx = -1, cur = 0, sp = 0;
+    QueryStats qs{0u, 0u};
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle != 0u && !exhausted && (idle == 0xffffffffu || __popc(idle) >= refill_thr)) {
+            const int leader = __ffs(idle) - 1;
+            unsigned int base = 0;
+            if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned int)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!active) {
+                idx = base + (unsigned int)__popc(idle & ((1u << lane) - 1u));
+                float tmax;
+                if (idx < n_rays && io.load(idx, o, d, tmax)) {
+                    invd = mk(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+                    ood = mk(o.x * invd.x, o.y * invd.y, o.z * invd.z);
+                    best_t = tmax; best_u = best_v = 0.f; best_pos = best_idx = -1;
+                    cur = 0; sp = 0;
+                    qs.visits = qs.tests = 0u;
+                    active = true;
+                    ++n_traced;
+                }
+            }
+            if (base + (unsigned int)__popc(idle) >= n_rays) exhausted = true;
+        }
+        unsigned act = __ballot_sync(0xffffffffu, active);
+        if (act == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        for (;;) {
+            bool fin = false, blocked = false;
+            Hit h;
+            while (active && !fin && cur >= 0)
+                if (!node_step<ANY, SMALL, STATS>(c, invd, ood, best_t, cur, sp, qs)) fin = true;
+            if (active && !fin) {  // leaf
+                const uint32_t code = (uint32_t)(~cur);
+                const int first = (int)(code >> 3), count = (int)(code & 7u) + 1;
+                for (int k = first; k < first + count; ++k) {
+                    V3 p1, e1, e2; int tidx, quad;
+                    load_tri<SMALL>(c, k, p1, e1, e2, tidx, quad);
+                    float t, u, v;
+                    if (STATS) qs.tests++;
+                    if (!mt_core(o, d, p1, e1, e2, t, u, v)) continue;
+                    if (ANY) {
+                        if (t < best_t) { best_t = t; best_u = u; best_v = v; best_pos = k; best_idx = tidx; blocked = true; break; }
+                    } else if (t < best_t || (t == best_t && best_idx >= 0 && tidx < best_idx)) {
+                        best_t = t; best_u = u; best_v = v; best_pos = k; best_idx = tidx;
+                    }
+                }
+                if (blocked || !stack_pop<ANY>(c, sp, cur, best_t)) fin = true;
+            }
+            if (active && fin) {
+                const bool hit = ANY ? blocked : best_idx >= 0;
+                h.t = best_t; h.u = best_u; h.v = best_v; h.pos = best_pos; h.idx = hit ? best_idx : -1;
+                io.store(idx, hit, h, qs);
+                if (STATS) { total.visits += qs.visits; total.tests += qs.tests; }
+                active = false;
+            }
+            act = __ballot_sync(0xffffffffu, active);
+            if (act == 0u) break;
+            if (!exhausted && 32 - __popc(act) >= refill_thr) break;
+        }
+    }
+}
+
+struct ExtendIO {
+    const float4* qo;
+    const float4* qd;
+    float4* hit;
+    ptb_pixel_stats* slot_stats;
+    int depth;
+    int slot;  // of the ray this lane holds
+    PTD_FI bool load(unsigned int i, V3& o, V3& d, float& tmax) {
+        const float4 a = qo[i], b = qd[i];
+        o = xyz(a); d = xyz(b);
+        slot = __float_as_int(a.w);
+        tmax = 1e20f;
+        return true;
+    }
+};
+
+template <bool SMALL, bool STATS>
+struct ExtendStore : ExtendIO {
+    const Ctx* c;
+    PTD_FI void store(unsigned int i, bool hit_any, const Hit& h, const QueryStats& qs) {
+        hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(hit_any ? h.pos : -1));
+        if constexpr (STATS) {
+            ptb_pixel_stats* s = slot_stats + slot;
+            if (depth == 0) {
+                int quad = -1;
+                if (hit_any) {
+                    V3 p1, e1, e2; int idx;
+                    load_tri<SMALL>(*c, h.pos, p1, e1, e2, idx, quad);
+                }
+                s->tri = hit_any ? h.idx : -1;
+                s->quad = quad;
+                s->t_bits = hit_any ? __float_as_uint(h.t) : 0u;
+                s->visits_primary = qs.visits;
+            } else {
+                s->visits_secondary += qs.visits;
+                s->id_hash = s->id_hash * 31u + (uint32_t)((hit_any ? h.idx : -1) + 2);
+            }
+            s->tri_tests += qs.tests;
+        }
+    }
+};
+
+template <bool SMALL, bool STATS>
+__global__ void __launch_bounds__(128) wf_extend_p(const SceneDev sc, const WfBuffers w, const int depth, const int qi,
+                                                   unsigned long long* counters, const int refill_thr) {
+    const unsigned int n = w.counts[depth];
+    if (blockIdx.x * blockDim.x >= n) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Ctx c = stage_scene<true, SMALL>(sc, smem);
+    ExtendStore<SMALL, STATS> io;
+    io.qo = w.q_o[qi]; io.qd = w.q_d[qi]; io.hit = w.hit; io.slot_stats = w.slot_stats; io.depth = depth; io.slot = 0;
+    io.c = &c;
+    uint32_t nrays = 0;
+    QueryStats total{0u, 0u};
+    trace_persistent<false, SMALL, STATS>(c, io, n, w.work + depth, refill_thr, nrays, total);
+    flush_counter(counters, CTR_CLOSEST, nrays);
+    if (STATS) {
+        flush_counter(counters, CTR_NODES, total.visits);
+        flush_counter(counters, CTR_TESTS, total.tests);
+    }
+}
+
+template <int MODE, bool STATS>
+struct ShadowIO {
+    const RenderArgs* a;
+    const WfBuffers* w;
+    long long P;
+    PTD_FI bool load(unsigned int i, V3& o, V3& d, float& tmax) {
+        const float4 rw = w->sq_w[i];
+        if (!(rw.w >= 0.0f || rw.w != rw.w)) {  // hole
+            if (MODE == PTB_MODE_AO) w->sq_res[i] = -2;
+            return false;
+        }
+        if (MODE == PTB_MODE_AO) {
+            const V3 p = xyz(w->slot_p[(long long)i % P]);
+            const V3 wi = xyz(rw);
+            const Ray s = get_ray(add(p, mul(wi, 0.01f)), wi);
+            o = s.o; d = s.d;
+        } else {
+            o = xyz(rw);
+            d = xyz(w->sq_d[i]);
+        }
+        tmax = rw.w;
+        return true;
+    }
+    PTD_FI void store(unsigned int i, bool occ, const Hit& h, const QueryStats& qs) {
+        const int res = occ ? h.idx : -1;
+        if (MODE == PTB_MODE_AO) {
+            w->sq_res[i] = res;
+            if constexpr (STATS) { w->sq_visits[i] = qs.visits; w->sq_tests[i] = qs.tests; }
+        } else {
+            V3 col = xyz(w->slot_p[i]);
+            if (!occ) {
+                const V3 cc = xyz(w->sq_c[i]);
+                col = mk(col.x + cc.x, col.y + cc.y, col.z + cc.z);
+            }
+            a->samples[i] = make_float4(cl_max(col.x, 0.0f), cl_max(col.y, 0.0f), cl_max(col.z, 0.0f), 1.0f);
+            if constexpr (STATS) {
+                ptb_pixel_stats* s = w->slot_stats + i;
+                s->visits_secondary += qs.visits;
+                s->id_hash = s->id_hash * 31u + (uint32_t)(res + 2);
+                s->tri_tests += qs.tests;
+                if (!occ) s->count = 1;
+            }
+        }
+    }
+};
+
+template <int MODE, bool SMALL, bool STATS>
+__global__ void __launch_bounds__(128) wf_shadow_p(const SceneDev sc, const RenderArgs a, const WfBuffers w,
+                                                   const unsigned int n_rays, unsigned int* work,
+                                                   unsigned long long* counters, const int refill_thr) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Ctx c = stage_scene<true, SMALL>(sc, smem);
+    ShadowIO<MODE, STATS> io;
+    io.a = &a; io.w = &w; io.P = (long long)a.frames_in_batch * a.n_local;
+    uint32_t nrays = 0;
+    QueryStats total{0u, 0u};
+    trace_persistent<true, SMALL, STATS>(c, io, n_rays, work, refill_thr, nrays, total);
+    flush_counter(counters, CTR_ANY, nrays);
+    if (STATS) {
+        flush_counter(counters, CTR_NODES, total.visits);
+        flush_counter(counters, CTR_TESTS, total.tests);
     }
 }
 
@@ -404,10 +612,19 @@ static int wf_smem(K kernel, size_t smem) {
 
 template <bool BVH, bool SMALL, bool STATS>
 static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArgs& a, const WfBuffers& w,
-                  unsigned long long* counters, uint64_t* launches) {
+                  unsigned long long* counters, uint64_t* launches, int sm_count) {
     const long long P = (long long)a.frames_in_batch * a.n_local;
     const int block = 128;
     const unsigned grid = (unsigned)((P + block - 1) / block);
+    const bool persist = BVH && a.tune[6] == 0;            // tune[6]=1: one thread per ray (no dynamic fetch)
+    const int refill_thr = a.tune[7] > 0 ? a.tune[7] : 8;  // idle lanes that trigger a refill
+    auto pgrid = [&](auto kernel, size_t smem, long long n_items) -> unsigned {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        long long g = (long long)per_sm * sm_count;
+        const long long need = (n_items + block - 1) / block;
+        return (unsigned)(g < need ? g : need);
+    };
     const size_t smem_q = scene_smem_bytes(sc, BVH, SMALL, block);
     const size_t smem_s = scene_smem_bytes(sc, false, SMALL, block);
     int rc;
@@ -419,15 +636,25 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
     if (mode == PTB_MODE_PATH) {
         auto shade = wf_shade_path<BVH, SMALL, STATS>;
         if ((rc = wf_smem(shade, smem_s))) return rc;
+        auto extp = wf_extend_p<SMALL, STATS>;
+        if (persist && (rc = wf_smem(extp, smem_q))) return rc;
+        const unsigned pg = persist ? pgrid(extp, smem_q, P) : 0u;
         for (int depth = 0; depth < a.max_depth; ++depth) {
             const int qi = depth & 1;
-            ext<<<grid, block, smem_q, st>>>(sc, w, depth, qi, counters);
+            if (persist) extp<<<pg, block, smem_q, st>>>(sc, w, depth, qi, counters, refill_thr);
+            else ext<<<grid, block, smem_q, st>>>(sc, w, depth, qi, counters);
             shade<<<grid, block, smem_s, st>>>(sc, a, w, depth, qi);
             *launches += 2;
         }
         WF_TRY(cudaGetLastError());
     } else {
-        ext<<<grid, block, smem_q, st>>>(sc, w, 0, 0, counters);
+        if (persist) {
+            auto extp = wf_extend_p<SMALL, STATS>;
+            if ((rc = wf_smem(extp, smem_q))) return rc;
+            extp<<<pgrid(extp, smem_q, P), block, smem_q, st>>>(sc, w, 0, 0, counters, refill_thr);
+        } else {
+            ext<<<grid, block, smem_q, st>>>(sc, w, 0, 0, counters);
+        }
         WF_TRY(cudaGetLastError());
         *launches += mode == PTB_MODE_PRIMARY ? 2 : (mode == PTB_MODE_AO ? 4 : 3);
         if (mode == PTB_MODE_PRIMARY) {
@@ -439,17 +666,29 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
             if ((rc = wf_smem(k, smem_s))) return rc;
             k<<<grid, block, smem_s, st>>>(sc, a, w);
             const long long nr = P * a.ao_samples;
-            auto sh = wf_shadow<PTB_MODE_AO, BVH, SMALL, STATS>;
-            if ((rc = wf_smem(sh, smem_q))) return rc;
-            sh<<<(unsigned)((nr + block - 1) / block), block, smem_q, st>>>(sc, a, w, nr, counters);
+            if (persist) {
+                auto shp = wf_shadow_p<PTB_MODE_AO, SMALL, STATS>;
+                if ((rc = wf_smem(shp, smem_q))) return rc;
+                shp<<<pgrid(shp, smem_q, nr), block, smem_q, st>>>(sc, a, w, (unsigned int)nr, w.work + 1, counters, refill_thr);
+            } else {
+                auto sh = wf_shadow<PTB_MODE_AO, BVH, SMALL, STATS>;
+                if ((rc = wf_smem(sh, smem_q))) return rc;
+                sh<<<(unsigned)((nr + block - 1) / block), block, smem_q, st>>>(sc, a, w, nr, counters);
+            }
             wf_finish_ao<STATS><<<(unsigned)((P + 255) / 256), 256, 0, st>>>(a, w);
         } else {
             auto k = wf_shade_first<PTB_MODE_DIRECT, BVH, SMALL, STATS>;
             if ((rc = wf_smem(k, smem_s))) return rc;
             k<<<grid, block, smem_s, st>>>(sc, a, w);
-            auto sh = wf_shadow<PTB_MODE_DIRECT, BVH, SMALL, STATS>;
-            if ((rc = wf_smem(sh, smem_q))) return rc;
-            sh<<<grid, block, smem_q, st>>>(sc, a, w, P, counters);
+            if (persist) {
+                auto shp = wf_shadow_p<PTB_MODE_DIRECT, SMALL, STATS>;
+                if ((rc = wf_smem(shp, smem_q))) return rc;
+                shp<<<pgrid(shp, smem_q, P), block, smem_q, st>>>(sc, a, w, (unsigned int)P, w.work + 1, counters, refill_thr);
+            } else {
+                auto sh = wf_shadow<PTB_MODE_DIRECT, BVH, SMALL, STATS>;
+                if ((rc = wf_smem(sh, smem_q))) return rc;
+                sh<<<grid, block, smem_q, st>>>(sc, a, w, P, counters);
+            }
         }
         WF_TRY(cudaGetLastError());
     }
@@ -464,7 +703,7 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
 // scratch layout for one batch; (re)allocates *scratch when it is too small
 static int wavefront_render(cudaStream_t st, void** scratch, size_t* scratch_bytes, unsigned long long* counters,
                             int mode, const SceneDev& sc, const RenderArgs& a, bool bvh, bool small, bool stats,
-                            int /*sm_count*/, uint64_t* launches) {
+                            int sm_count, uint64_t* launches) {
     const size_t P = (size_t)a.frames_in_batch * a.n_local;
     const size_t n_shadow = mode == PTB_MODE_AO ? P * (size_t)a.ao_samples : (mode == PTB_MODE_DIRECT ? P : 0);
     const size_t n_counts = (size_t)a.max_depth + 2;
@@ -483,7 +722,7 @@ static int wavefront_render(cudaStream_t st, void** scratch, size_t* scratch_byt
     const size_t o_vis = take(mode == PTB_MODE_AO && stats ? n_shadow * 4 : 0);
     const size_t o_tst = take(mode == PTB_MODE_AO && stats ? n_shadow * 4 : 0);
     const size_t o_stats = take(stats ? P * sizeof(ptb_pixel_stats) : 0);
-    const size_t o_counts = take(n_counts * 4);
+    const size_t o_counts = take(n_counts * 4 * 2);  // queue lengths, then work counters
     if (*scratch_bytes < off) {
         if (*scratch) WF_TRY(cudaFree(*scratch));
         *scratch = nullptr; *scratch_bytes = 0;
@@ -501,8 +740,11 @@ static int wavefront_render(cudaStream_t st, void** scratch, size_t* scratch_byt
     w.sq_res = (int*)(base + o_res); w.sq_visits = (uint32_t*)(base + o_vis); w.sq_tests = (uint32_t*)(base + o_tst);
     w.slot_stats = (ptb_pixel_stats*)(base + o_stats);
     w.counts = (unsigned int*)(base + o_counts);
-    WF_TRY(cudaMemsetAsync(w.counts, 0, n_counts * 4, st));
-#define WF_CASE(B, S, T) if (bvh == B && small == S && stats == T) return wf_run<B, S, T>(st, mode, sc, a, w, counters, launches)
+    w.work = w.counts + n_counts;
+    WF_TRY(cudaMemsetAsync(w.counts, 0, n_counts * 4 * 2, st));
+    if (P * (mode == PTB_MODE_AO ? (size_t)a.ao_samples : 1) >= 0xffffffffull)
+        return ptb::fail(PTB_E_INVALID, "wavefront_render: batch too large for 32-bit ray indices; lower frames_per_batch");
+#define WF_CASE(B, S, T) if (bvh == B && small == S && stats == T) return wf_run<B, S, T>(st, mode, sc, a, w, counters, launches, sm_count)
     WF_CASE(true, true, false); WF_CASE(true, true, true); WF_CASE(true, false, false); WF_CASE(true, false, true);
     WF_CASE(false, true, false); WF_CASE(false, true, true); WF_CASE(false, false, false); WF_CASE(false, false, true);
 #undef WF_CASE

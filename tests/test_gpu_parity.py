@@ -437,3 +437,22 @@ def test_path_regeneration_equals_one_sample_per_thread(dev, pt, scene):
     finally:
         dev.set_tuning(5, 0)
     assert res[0] == res[1]
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_wavefront_persistent_fetch_is_scheduling_only(dev, pt, scene, mode):
+    """tune[6]/tune[7]: persistent traversal with dynamic ray fetch (any refill threshold) vs one thread per ray."""
+    kw = dict(width=250, height=90, n_frames=3, mode=mode, accum=pt.ACCUM_LINEAR, max_depth=7, collect_stats=1,
+              integrator=pt.INTEGRATOR_WAVEFRONT, frames_per_batch=2, ao_samples=5)
+    res = []
+    try:
+        for persist_off, thr in ((1, 0), (0, 1), (0, 8), (0, 20), (0, 32)):
+            dev.set_tuning(6, persist_off); dev.set_tuning(7, thr)
+            frame, stats = dev.buffer(250 * 90 * 16), dev.buffer(250 * 90 * 32)
+            ctr = dev.render(scene, pt.default_params(**kw), frame, stats, want_counters=True)
+            res.append((frame.read(np.uint32).tobytes(), stats.read(np.uint32).tobytes(), tuple(sorted(ctr.items()))))
+            frame.close(); stats.close()
+    finally:
+        dev.set_tuning(6, 0); dev.set_tuning(7, 0)
+    for r in res[1:]:
+        assert r == res[0]
