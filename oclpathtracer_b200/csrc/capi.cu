@@ -581,8 +581,14 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
     a.counters = dev->counters;
     for (int k = 0; k < 8; ++k) a.tune[k] = dev->tune[k];
 
+    // AUTO = the faster integrator as measured on B200: the wavefront wins where paths
+    // of very different length share a warp (PATH on a shared-memory-resident scene, >= 1 M samples in
+    // flight); the megakernel wins for the fixed-shape modes and for scenes traversed from L2/HBM.
     int integrator = p->integrator;
-    if (integrator == PTB_INTEGRATOR_AUTO) integrator = PTB_INTEGRATOR_MEGAKERNEL;
+    if (integrator == PTB_INTEGRATOR_AUTO) {
+        const bool wf = p->mode == PTB_MODE_PATH && small && bvh && (long long)fpb * n_local >= (1ll << 20);
+        integrator = wf ? PTB_INTEGRATOR_WAVEFRONT : PTB_INTEGRATOR_MEGAKERNEL;
+    }
 
     for (int f0 = 0; f0 < p->n_frames; f0 += fpb) {
         const int nb = (p->n_frames - f0 < fpb) ? p->n_frames - f0 : fpb;
