@@ -94,6 +94,17 @@ int ptb_kernel_set_int(ptb_kernel* k, const char* name, int value);
 int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* bufs, int n_bufs, const void* consts,
                  size_t const_bytes, int n_threads, int local_size);
 
+/* Launch capture / replay: Launcher::serializeToFile / deserializeFromFile
+ * (Adl/AdlKernel.h:185-188, Adl/CL/AdlKernelUtilsCL.cpp:509-620).  Same byte layout as the reference writes:
+ * int32 nArgs; per argument { int32 isBuffer; int32 sizeInBytes; bytes }; then ExecInfo
+ * { int32 nWIs[3]; int32 wgSize[3]; int32 nDim } -- so a dump taken from the reference's OpenCL run of
+ * GenerateColors replays here.  _serialize reads the buffers back (it synchronises); _deserialize creates one
+ * ptb_buffer per buffer argument (caller destroys them) and returns the by-value block and the launch shape. */
+int ptb_launch_serialize(ptb_device* dev, const char* path, ptb_buffer* const* bufs, int n_bufs, const void* consts,
+                         size_t const_bytes, int n_threads, int local_size);
+int ptb_launch_deserialize(ptb_device* dev, const char* path, ptb_buffer** bufs_out, int buf_cap, int* n_bufs,
+                           void* consts_out /* >= 64 bytes */, size_t* const_bytes, int* n_threads, int* local_size);
+
 /* ---- host-side scene helpers: RaytraceTest.cpp:87-198 loadModel -------------------- */
 int ptb_load_model(const char* path, ptb_triangle** tris, int* n_tris, ptb_material** mats, int* n_mats);
 /* BUILD-DEFINED C5 scene: each quad (triangle pair) -> k x k sub-quads */

@@ -82,7 +82,7 @@ EXPORTS = [
     "ptb_device_destroy", "ptb_device_sync", "ptb_device_name", "ptb_device_sm_count", "ptb_device_stream",
     "ptb_buffer_create", "ptb_buffer_wrap", "ptb_buffer_destroy", "ptb_buffer_write", "ptb_buffer_read",
     "ptb_buffer_map", "ptb_buffer_unmap", "ptb_buffer_clear", "ptb_buffer_device_ptr", "ptb_buffer_size",
-    "ptb_kernel_get", "ptb_kernel_set_int", "ptb_launch1d", "ptb_load_model", "ptb_tessellate",
+    "ptb_kernel_get", "ptb_kernel_set_int", "ptb_launch1d", "ptb_launch_serialize", "ptb_launch_deserialize", "ptb_load_model", "ptb_tessellate",
     "ptb_light_from_quad", "ptb_free", "ptb_to_rgb8", "ptb_write_ppm", "ptb_bvh_params_default",
     "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_copy_bvh",
     "ptb_render_params_default", "ptb_render_local_pixels", "ptb_render", "ptb_render_host",
@@ -138,6 +138,8 @@ def lib():
         L.ptb_kernel_get.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p]
         L.ptb_kernel_set_int.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.ptb_launch1d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+        L.ptb_launch_serialize.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+        L.ptb_launch_deserialize.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.ptb_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 9
         L.ptb_device_profile.argtypes = [C.c_void_p, C.c_int]
         L.ptb_device_profile_read.argtypes = [C.c_void_p] * 5
@@ -362,6 +364,27 @@ class Device:
         arr = (C.c_void_p * len(bufs))(*[b._h for b in bufs])
         _check(lib().ptb_launch1d(self._h, kernel, arr, len(bufs), C.byref(consts), C.sizeof(consts), n_threads,
                                   local_size))
+
+    def launch_serialize(self, path, bufs, consts, n_threads, local_size=64):
+        arr = (C.c_void_p * len(bufs))(*[b._h for b in bufs])
+        _check(lib().ptb_launch_serialize(self._h, path.encode(), arr, len(bufs), C.byref(consts), C.sizeof(consts),
+                                          n_threads, local_size))
+
+    def launch_deserialize(self, path, cap=8):
+        """-> (buffers, const block bytes, n_threads, local_size); the buffers belong to the caller."""
+        handles = (C.c_void_p * cap)()
+        nb, cb, nt, ls = C.c_int(), C.c_size_t(), C.c_int(), C.c_int()
+        consts = C.create_string_buffer(64)
+        _check(lib().ptb_launch_deserialize(self._h, path.encode(), handles, cap, C.byref(nb), consts, C.byref(cb),
+                                            C.byref(nt), C.byref(ls)))
+        bufs = []
+        for i in range(nb.value):
+            b = Buffer.__new__(Buffer)
+            b.dev, b._h = self, C.c_void_p(handles[i])
+            b.nbytes = lib().ptb_buffer_size(b._h)
+            self._children.append(b)
+            bufs.append(b)
+        return bufs, consts.raw[: cb.value], nt.value, ls.value
 
     def trace(self, scene, o, d, tmax, accel=ACCEL_BVH, any_hit=False):
         n = len(o)

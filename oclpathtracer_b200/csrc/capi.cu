@@ -903,6 +903,87 @@ extern "C" int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* b
     return render_impl(dev, k->scene, &p, static_cast<float4*>(fb->d_ptr), fb->bytes, nullptr, 0, nullptr);
 }
 
+// ---- launch capture / replay (Launcher::serializeToFile / deserializeFromFile) ---------------------------------
+
+extern "C" int ptb_launch_serialize(ptb_device* dev, const char* path, ptb_buffer* const* bufs, int n_bufs,
+                                    const void* consts, size_t const_bytes, int n_threads, int local_size) {
+    if (!dev || !path || !bufs || n_bufs < 0 || (!consts && const_bytes)) return fail(PTB_E_INVALID, "ptb_launch_serialize: bad arguments");
+    if (const_bytes > 64) return fail(PTB_E_INVALID, "ptb_launch_serialize: constant block larger than MAX_ARG_SIZE (64)");
+    if (set_device(dev)) return PTB_E_CUDA;
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(PTB_E_IO, "ptb_launch_serialize: cannot open %s", path);
+    auto put_i = [&](int32_t v) { std::fwrite(&v, 4, 1, f); };
+    put_i(n_bufs + (const_bytes ? 1 : 0));
+    std::vector<char> host;
+    for (int i = 0; i < n_bufs; ++i) {
+        put_i(1);
+        const size_t nb = bufs[i] ? bufs[i]->bytes : 0;
+        if (nb > 0x7fffffffu) { std::fclose(f); return fail(PTB_E_INVALID, "ptb_launch_serialize: buffer %d exceeds the format's 31-bit size", i); }
+        put_i((int32_t)nb);
+        if (nb) {
+            host.resize(nb);
+            cudaError_t e = cudaMemcpyAsync(host.data(), bufs[i]->d_ptr, nb, cudaMemcpyDeviceToHost, dev->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(dev->stream);
+            if (e != cudaSuccess) { std::fclose(f); return fail(PTB_E_CUDA, "ptb_launch_serialize: read-back failed: %s", cudaGetErrorString(e)); }
+            std::fwrite(host.data(), 1, nb, f);
+        }
+    }
+    if (const_bytes) {
+        put_i(0);
+        put_i((int32_t)const_bytes);
+        std::fwrite(consts, 1, const_bytes, f);
+    }
+    const int32_t info[7] = {n_threads, 1, 1, local_size, 1, 1, 1};  // Launcher::ExecInfo (Adl/AdlKernel.h:139-160)
+    std::fwrite(info, 4, 7, f);
+    const bool ok = std::ferror(f) == 0;
+    std::fclose(f);
+    return ok ? PTB_OK : fail(PTB_E_IO, "ptb_launch_serialize: write error on %s", path);
+}
+
+extern "C" int ptb_launch_deserialize(ptb_device* dev, const char* path, ptb_buffer** bufs_out, int buf_cap, int* n_bufs,
+                                      void* consts_out, size_t* const_bytes, int* n_threads, int* local_size) {
+    if (!dev || !path || !bufs_out || !n_bufs || !consts_out || !const_bytes || !n_threads || !local_size)
+        return fail(PTB_E_INVALID, "ptb_launch_deserialize: null argument");
+    *n_bufs = 0; *const_bytes = 0;
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(PTB_E_IO, "ptb_launch_deserialize: cannot open %s", path);
+    auto bail = [&](int code, const char* what) {
+        std::fclose(f);
+        for (int i = 0; i < *n_bufs; ++i) ptb_buffer_destroy(bufs_out[i]);
+        *n_bufs = 0;
+        return fail(code, "ptb_launch_deserialize: %s in %s", what, path);
+    };
+    int32_t n_args = 0;
+    if (std::fread(&n_args, 4, 1, f) != 1 || n_args < 0 || n_args > 64) return bail(PTB_E_IO, "bad argument count");
+    std::vector<char> data;
+    for (int i = 0; i < n_args; ++i) {
+        int32_t is_buf = 0, nb = 0;
+        if (std::fread(&is_buf, 4, 1, f) != 1 || std::fread(&nb, 4, 1, f) != 1 || nb < 0) return bail(PTB_E_IO, "truncated argument header");
+        data.resize((size_t)nb);
+        if (nb && std::fread(data.data(), 1, (size_t)nb, f) != (size_t)nb) return bail(PTB_E_IO, "truncated argument data");
+        if (is_buf) {
+            if (*n_bufs >= buf_cap) return bail(PTB_E_INVALID, "more buffer arguments than buf_cap");
+            ptb_buffer* b = nullptr;
+            if (int rc = ptb_buffer_create(dev, (size_t)nb, &b)) { std::fclose(f); return rc; }
+            bufs_out[(*n_bufs)++] = b;
+            if (nb) {
+                if (int rc = ptb_buffer_write(b, data.data(), (size_t)nb, 0)) { std::fclose(f); return rc; }
+                cudaStreamSynchronize(dev->stream);  // `data` is reused for the next argument
+            }
+        } else {
+            if (nb > 64) return bail(PTB_E_IO, "constant block larger than 64 bytes");
+            std::memcpy(consts_out, data.data(), (size_t)nb);
+            *const_bytes = (size_t)nb;
+        }
+    }
+    int32_t info[7];
+    if (std::fread(info, 4, 7, f) != 7) return bail(PTB_E_IO, "truncated ExecInfo");
+    std::fclose(f);
+    *n_threads = info[0];
+    *local_size = info[3];
+    return PTB_OK;
+}
+
 // ---- measurement hooks -----------------------------------------------------------------------------------------
 
 extern "C" int ptb_device_set_tuning(ptb_device* dev, int index, int value) {

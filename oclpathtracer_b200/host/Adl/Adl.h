@@ -161,6 +161,33 @@ class Launcher {
         return 0.f;
     }
 
+    struct ExecInfo {  // reference Adl/AdlKernel.h:139-160
+        int m_nWIs[3];
+        int m_wgSize[3];
+        int m_nDim;
+        ExecInfo() {}
+        ExecInfo(int nWIsX, int nWIsY = 1, int nWIsZ = 1, int wgSizeX = 64, int wgSizeY = 1, int wgSizeZ = 1, int nDim = 1) {
+            m_nWIs[0] = nWIsX; m_nWIs[1] = nWIsY; m_nWIs[2] = nWIsZ;
+            m_wgSize[0] = wgSizeX; m_wgSize[1] = wgSizeY; m_wgSize[2] = wgSizeZ;
+            m_nDim = nDim;
+        }
+    };
+    // dump the bound arguments + buffer contents in the reference's own file layout (AdlKernelUtilsCL.cpp:509-563)
+    void serializeToFile(const char* filePath, const ExecInfo& info) {
+        if (m_deviceData) ptb_launch_serialize(m_deviceData->m_dev, filePath, m_bufs, m_nBufs, m_const, m_constBytes, info.m_nWIs[0], info.m_wgSize[0]);
+    }
+    // re-create the buffers of a dump and bind everything; the caller then launches with the returned shape
+    ExecInfo deserializeFromFile(const char* filePath, int buffCap, ptb_buffer** buffsOut, int* nBuffs) {
+        ExecInfo info(0);
+        int n = 0, ls = 64;
+        m_nBufs = 0;
+        if (m_deviceData && ptb_launch_deserialize(m_deviceData->m_dev, filePath, buffsOut, buffCap, nBuffs, m_const, &m_constBytes, &n, &ls) == PTB_OK) {
+            for (int i = 0; i < *nBuffs && i < MAX_ARG_COUNT; ++i) m_bufs[m_nBufs++] = buffsOut[i];
+            info = ExecInfo(n, 1, 1, ls);
+        }
+        return info;
+    }
+
   private:
     const Device* m_deviceData;
     const Kernel* m_kernel;

@@ -456,3 +456,39 @@ def test_wavefront_persistent_fetch_is_scheduling_only(dev, pt, scene, mode):
         dev.set_tuning(6, 0); dev.set_tuning(7, 0)
     for r in res[1:]:
         assert r == res[0]
+
+
+def test_launch_capture_and_replay(dev, pt, ob, cornell, tmp_path):
+    """Launcher::serializeToFile / deserializeFromFile analogue, in the reference's own file layout."""
+    import struct
+    tris, mats = cornell
+    w = h = 48
+    tb, mb, fb = dev.buffer(36 * 64), dev.buffer(18 * 64), dev.buffer(w * h * 16)
+    tb.write(tris); mb.write(mats)
+    k = dev.kernel("GenerateColors", "GenerateColors")
+    for frame in range(3):
+        dev.launch1d(k, [tb, mb, fb], pt.Int4(w, h, frame, 0), w * h)
+    dev.sync()
+    dump = str(tmp_path / "launch.bin")
+    dev.launch_serialize(dump, [tb, mb, fb], pt.Int4(w, h, 3, 0), w * h)   # state BEFORE frame 3
+    dev.launch1d(k, [tb, mb, fb], pt.Int4(w, h, 3, 0), w * h)
+    dev.sync()
+    direct = fb.read(np.uint32)
+    raw = open(dump, "rb").read()
+    assert struct.unpack_from("<i", raw, 0)[0] == 4 and struct.unpack_from("<ii", raw, 4) == (1, 36 * 64)
+    assert struct.unpack_from("<7i", raw, len(raw) - 28) == (w * h, 1, 1, 64, 1, 1, 1)
+    bufs, consts, n_threads, local = dev.launch_deserialize(dump)
+    assert len(bufs) == 3 and n_threads == w * h and local == 64 and struct.unpack("<4i", consts) == (w, h, 3, 0)
+    c = pt.Int4(*struct.unpack("<4i", consts))
+    dev.launch1d(k, bufs, c, n_threads, local)
+    dev.sync()
+    assert bufs[2].read(np.uint32).tobytes() == direct.tobytes()
+    want, _, _ = ob.render(ob.default_params(w, h, first_frame=0, n_frames=4, mode=3, accum=ob.ACCUM_REFERENCE), tris, mats)
+    assert direct.tobytes() == want.tobytes()
+    with pytest.raises(pt.PtbError, match="cannot open"):
+        dev.launch_deserialize(str(tmp_path / "nope.bin"))
+    (tmp_path / "short.bin").write_bytes(raw[:100])
+    with pytest.raises(pt.PtbError, match="truncated"):
+        dev.launch_deserialize(str(tmp_path / "short.bin"))
+    for b in bufs + [tb, mb, fb]:
+        b.close()
