@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--fpb", type=int, default=0, help="frames_per_batch override")
     ap.add_argument("--smem-nodes", type=int, default=0, help="BVH nodes staged in shared memory (0 = default)")
     ap.add_argument("--max-leaf", type=int, default=0, help="BVH max triangles per leaf (0 = default)")
+    ap.add_argument("--gpu-build", action="store_true", help="build the BVH on the device (LBVH) instead of the host SAH builder")
     ap.add_argument("--ab", action="store_true", help="also time the other integrator and brute force (extra keys)")
     return ap.parse_args()
 
@@ -253,7 +254,7 @@ def main():
             bp.smem_nodes = args.smem_nodes
         if args.max_leaf:
             bp.max_leaf = args.max_leaf
-    scene = dev.scene(tris, mats, bp)
+    scene = dev.scene(tris, mats, bp, gpu_build=args.gpu_build)
     dev.sync()
     build_s = time.perf_counter() - t0
     npix = wl["width"] * wl["height"]

@@ -131,6 +131,10 @@ int ptb_bvh_build_host(const ptb_triangle* tris, int n_tris, const ptb_bvh_param
 
 int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats, int n_mats,
                      const ptb_bvh_params* bvh_params /* NULL = default */, ptb_scene** out);
+/* same, but the BVH is built ON the device (Morton-order LBVH, csrc/lbvh.cuh): milliseconds for millions of
+ * triangles instead of seconds; lower tree quality than the host SAH build.  Needs >= 2 triangles.          */
+int ptb_scene_create_gpu(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats, int n_mats,
+                         const ptb_bvh_params* bvh_params /* NULL = default */, ptb_scene** out);
 int ptb_scene_destroy(ptb_scene* scene);
 int ptb_scene_info(ptb_scene* scene, int* n_nodes, int* n_tris, int* depth, int* smem_nodes);
 /* host copies of the built tree, for structural validation and the oracle */

@@ -84,7 +84,7 @@ EXPORTS = [
     "ptb_buffer_map", "ptb_buffer_unmap", "ptb_buffer_clear", "ptb_buffer_device_ptr", "ptb_buffer_size",
     "ptb_kernel_get", "ptb_kernel_set_int", "ptb_launch1d", "ptb_launch_serialize", "ptb_launch_deserialize", "ptb_load_model", "ptb_tessellate",
     "ptb_light_from_quad", "ptb_free", "ptb_to_rgb8", "ptb_write_ppm", "ptb_bvh_params_default",
-    "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_copy_bvh",
+    "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_create_gpu", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_copy_bvh",
     "ptb_render_params_default", "ptb_render_local_pixels", "ptb_render", "ptb_render_host",
     "ptb_render_host_async", "ptb_job_wait", "ptb_host_alloc", "ptb_host_free", "ptb_trace",
     "ptb_device_profile", "ptb_device_profile_read", "ptb_device_set_tuning", "ptb_test_sincos", "ptb_test_pow", "ptb_test_rng", "ptb_test_camera",
@@ -125,6 +125,7 @@ def lib():
         L.ptb_device_stream.argtypes = [C.c_void_p]
         L.ptb_bvh_build_host.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
         L.ptb_scene_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ptb_scene_create_gpu.argtypes = L.ptb_scene_create.argtypes
         L.ptb_scene_info.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.ptb_scene_copy_bvh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ptb_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -312,8 +313,8 @@ class Device:
     def wrap(self, device_ptr, nbytes):
         return Buffer(self, nbytes, device_ptr=device_ptr)
 
-    def scene(self, tris, mats, bvh_params=None):
-        return Scene(self, tris, mats, bvh_params)
+    def scene(self, tris, mats, bvh_params=None, gpu_build=False):
+        return Scene(self, tris, mats, bvh_params, gpu_build)
 
     def close(self):
         if self._h:
@@ -469,12 +470,13 @@ class Buffer:
 class Scene:
     """Resident scene: relaid triangles + BVH (BUILD-DEFINED; the reference is brute force)."""
 
-    def __init__(self, dev, tris, mats, bvh_params=None):
+    def __init__(self, dev, tris, mats, bvh_params=None, gpu_build=False):
         self.dev = dev
         self._h = C.c_void_p()
         tris = np.ascontiguousarray(tris)
         mats = np.ascontiguousarray(mats)
-        _check(lib().ptb_scene_create(dev._h, _p(tris), len(tris), _p(mats), len(mats),
+        create = lib().ptb_scene_create_gpu if gpu_build else lib().ptb_scene_create
+        _check(create(dev._h, _p(tris), len(tris), _p(mats), len(mats),
                                       C.byref(bvh_params) if bvh_params is not None else None, C.byref(self._h)))
         dev._children.append(self)
 

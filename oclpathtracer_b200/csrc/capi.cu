@@ -2,6 +2,7 @@
 // kernel table + launcher, resident scene, and the render entry points that
 // drive the sm_100a kernels.  Replaces the ADL Device/Buffer/Launcher plumbing
 // (Adl/Adl.h, Adl/AdlKernel.h, Adl/CL/*) for this path.  No CPU fallback.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -13,6 +14,7 @@
 #include "host_internal.h"
 #include "pt_kernels.cuh"
 #include "pt_wavefront.cuh"
+#include "lbvh.cuh"
 
 namespace ptb {
 
@@ -105,6 +107,9 @@ struct ptb_scene {
     float4* d_tris_orig = nullptr;
     float4* d_mats = nullptr;
     bool small = false;
+    int n_nodes = 0, depth = 0, bfs_nodes = 0;
+    int* d_order = nullptr;               // GPU-built scenes: BVH position -> caller index (device)
+    bool host_copy_valid = true;          // false until a GPU-built tree has been downloaded
     std::vector<ptb_triangle> host_tris;  // kept for the default light lookup
 };
 
@@ -326,7 +331,7 @@ extern "C" int ptb_scene_destroy(ptb_scene* s) {
     if (!s) return PTB_OK;
     set_device(s->dev);
     cudaStreamSynchronize(s->dev->stream);
-    for (void* p : {(void*)s->d_nodes, (void*)s->d_tris, (void*)s->d_tris_orig, (void*)s->d_mats})
+    for (void* p : {(void*)s->d_nodes, (void*)s->d_tris, (void*)s->d_tris_orig, (void*)s->d_mats, (void*)s->d_order})
         if (p) cudaFree(p);
     delete s;
     return PTB_OK;
@@ -356,6 +361,7 @@ extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n
         std::memcpy(&tbits, &mats[i].type, 4);
         m[2 * i + 1] = make_float4(mats[i].emissive.x, mats[i].emissive.y, mats[i].emissive.z, tbits);
     }
+    s->n_nodes = int(s->bvh.nodes.size()); s->depth = s->bvh.depth; s->bfs_nodes = s->bvh.smem_nodes;
     const size_t staged = s->bvh.nodes.size() * 64 + size_t(n_tris) * 48 + size_t(n_mats) * 32;
     s->small = staged <= 32 * 1024 && int(s->bvh.nodes.size()) == s->bvh.smem_nodes;
     if (set_device(dev)) { delete s; return PTB_E_CUDA; }
@@ -372,6 +378,58 @@ extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n
     }
     // the host vectors `orig` and `m` die at return: finish the copies now
     CU_TRY(cudaStreamSynchronize(dev->stream));
+    *out = s;
+    return PTB_OK;
+}
+
+// Scene whose BVH is built on the device (lbvh.cuh).  Only the root is guaranteed to sit at index 0, so one
+// node is staged in shared memory; everything else is traversed from L2/HBM.
+extern "C" int ptb_scene_create_gpu(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats,
+                                    int n_mats, const ptb_bvh_params* bvh_params, ptb_scene** out) {
+    if (!dev || !tris || !mats || !out || n_tris < 2 || n_mats < 1)
+        return fail(PTB_E_INVALID, "ptb_scene_create_gpu: bad arguments (needs >= 2 triangles)");
+    *out = nullptr;
+    for (int i = 0; i < n_tris; ++i) {
+        if (tris[i].id < 0 || tris[i].id >= n_mats)
+            return fail(PTB_E_INVALID, "ptb_scene_create_gpu: triangle %d has id %d outside [0,%d)", i, tris[i].id, n_mats);
+        const float* v = &tris[i].p1.x;
+        for (int k = 0; k < 12; ++k)
+            if (!(std::fabs(v[k]) <= 3.0e38f)) return fail(PTB_E_INVALID, "ptb_scene_create_gpu: triangle %d has a non-finite vertex", i);
+    }
+    ptb_bvh_params bp;
+    if (bvh_params) bp = *bvh_params; else ptb_bvh_params_default(&bp);
+    if (set_device(dev)) return PTB_E_CUDA;
+    ptb_scene* s = new ptb_scene();
+    s->dev = dev; s->n_tris = n_tris; s->n_mats = n_mats;
+    s->host_tris.assign(tris, tris + n_tris);
+    s->host_copy_valid = false;
+    std::vector<ptb_bvh_tri> orig;
+    make_edge_tris(tris, n_tris, &orig);
+    std::vector<float4> m(size_t(n_mats) * 2);
+    for (int i = 0; i < n_mats; ++i) {
+        m[2 * i] = make_float4(mats[i].albedo.x, mats[i].albedo.y, mats[i].albedo.z, mats[i].roughness);
+        float tbits;
+        std::memcpy(&tbits, &mats[i].type, 4);
+        m[2 * i + 1] = make_float4(mats[i].emissive.x, mats[i].emissive.y, mats[i].emissive.z, tbits);
+    }
+    ptb_triangle* d_raw = nullptr;
+    int rc = PTB_OK;
+    auto fail_out = [&](int code) { if (d_raw) cudaFree(d_raw); ptb_scene_destroy(s); return code; };
+    if (cudaMalloc((void**)&d_raw, size_t(n_tris) * 64) != cudaSuccess) return fail_out(fail(PTB_E_NOMEM, "ptb_scene_create_gpu: cudaMalloc failed"));
+    if (cudaMemcpyAsync(d_raw, tris, size_t(n_tris) * 64, cudaMemcpyHostToDevice, dev->stream) != cudaSuccess)
+        return fail_out(fail(PTB_E_CUDA, "ptb_scene_create_gpu: upload failed"));
+    float4* d_nodes = nullptr; float4* d_otris = nullptr; int* d_order = nullptr; int depth = 0;
+    if ((rc = ptd::build_lbvh_device(dev->stream, d_raw, n_tris, bp.max_leaf, bp.pad_rel, &d_nodes, &d_otris, &d_order, &depth))) return fail_out(rc);
+    s->d_nodes = d_nodes; s->d_tris = d_otris; s->d_order = d_order;
+    s->n_nodes = n_tris - 1; s->depth = depth; s->bfs_nodes = 1; s->small = false;
+    auto up = [&](float4** d, const void* h, size_t bytes) -> int {
+        CU_TRY(cudaMalloc((void**)d, bytes));
+        CU_TRY(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, dev->stream));
+        return PTB_OK;
+    };
+    if ((rc = up(&s->d_tris_orig, orig.data(), orig.size() * 48)) || (rc = up(&s->d_mats, m.data(), m.size() * 16))) return fail_out(rc);
+    if (cudaStreamSynchronize(dev->stream) != cudaSuccess) return fail_out(fail(PTB_E_CUDA, "ptb_scene_create_gpu: sync failed"));
+    cudaFree(d_raw);
     *out = s;
     return PTB_OK;
 }
@@ -402,15 +460,24 @@ extern "C" int ptb_bvh_build_host(const ptb_triangle* tris, int n_tris, const pt
 
 extern "C" int ptb_scene_info(ptb_scene* s, int* n_nodes, int* n_tris, int* depth, int* smem_nodes) {
     if (!s) return fail(PTB_E_INVALID, "ptb_scene_info: null scene");
-    if (n_nodes) *n_nodes = int(s->bvh.nodes.size());
+    if (n_nodes) *n_nodes = s->n_nodes;
     if (n_tris) *n_tris = s->n_tris;
-    if (depth) *depth = s->bvh.depth;
-    if (smem_nodes) *smem_nodes = s->bvh.smem_nodes;
+    if (depth) *depth = s->depth;
+    if (smem_nodes) *smem_nodes = s->bfs_nodes;
     return PTB_OK;
 }
 
 extern "C" int ptb_scene_copy_bvh(ptb_scene* s, ptb_bvh_node* nodes, int32_t* tri_order) {
     if (!s) return fail(PTB_E_INVALID, "ptb_scene_copy_bvh: null scene");
+    if (!s->host_copy_valid) {  // GPU-built tree: download on first request
+        if (set_device(s->dev)) return PTB_E_CUDA;
+        s->bvh.nodes.resize(size_t(s->n_nodes));
+        s->bvh.tri_order.resize(size_t(s->n_tris));
+        CU_TRY(cudaMemcpyAsync(s->bvh.nodes.data(), s->d_nodes, size_t(s->n_nodes) * 64, cudaMemcpyDeviceToHost, s->dev->stream));
+        CU_TRY(cudaMemcpyAsync(s->bvh.tri_order.data(), s->d_order, size_t(s->n_tris) * 4, cudaMemcpyDeviceToHost, s->dev->stream));
+        CU_TRY(cudaStreamSynchronize(s->dev->stream));
+        s->host_copy_valid = true;
+    }
     if (nodes) std::memcpy(nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptb_bvh_node));
     if (tri_order) std::memcpy(tri_order, s->bvh.tri_order.data(), s->bvh.tri_order.size() * sizeof(int32_t));
     return PTB_OK;
@@ -419,14 +486,14 @@ extern "C" int ptb_scene_copy_bvh(ptb_scene* s, ptb_bvh_node* nodes, int32_t* tr
 static ptd::SceneDev scene_dev(const ptb_scene* s) {
     ptd::SceneDev d;
     d.nodes = s->d_nodes; d.tris = s->d_tris; d.tris_orig = s->d_tris_orig; d.mats = s->d_mats;
-    d.n_nodes = int(s->bvh.nodes.size()); d.n_tris = s->n_tris; d.n_mats = s->n_mats;
+    d.n_nodes = s->n_nodes; d.n_tris = s->n_tris; d.n_mats = s->n_mats;
     // Large scenes stage only the top of the tree: a 64-node (4 KB) prefix keeps >= 6 CTAs per SM
     // resident next to the traversal stack (measured on the 2M-triangle scene: 1024 nodes 0.83,
     // 256 nodes 1.81, 64 nodes 2.28 Grays/s).
     const int cap = s->dev->tune[4] > 0 ? s->dev->tune[4] : 64;
-    d.smem_nodes = s->small ? s->bvh.smem_nodes : (s->bvh.smem_nodes < cap ? s->bvh.smem_nodes : cap);
+    d.smem_nodes = s->small ? s->bfs_nodes : (s->bfs_nodes < cap ? s->bfs_nodes : cap);
     d.small = s->small ? 1 : 0;
-    d.stack_depth = s->bvh.depth + 1;
+    d.stack_depth = s->depth + 1;
     return d;
 }
 

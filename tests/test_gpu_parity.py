@@ -492,3 +492,88 @@ def test_launch_capture_and_replay(dev, pt, ob, cornell, tmp_path):
         dev.launch_deserialize(str(tmp_path / "short.bin"))
     for b in bufs + [tb, mb, fb]:
         b.close()
+
+
+def _check_tree(nodes, order, tris, pad_min):
+    """every triangle reachable exactly once from the root; every child box contains its triangles (+pad)."""
+    n = len(tris)
+    tri_lo = np.minimum(np.minimum(tris["p1"], tris["p2"]), tris["p3"])[:, :3]
+    tri_hi = np.maximum(np.maximum(tris["p1"], tris["p2"]), tris["p3"])[:, :3]
+    covered = np.zeros(n, np.int32)
+    stack = [(0, None, None)]
+    depth_max = 0
+    work = [(0, 1)]
+    bounds = {}
+    # iterative post-order: compute subtree bounds
+    order_stack, visit = [0], []
+    while order_stack:
+        ni = order_stack.pop()
+        visit.append(ni)
+        for ch in (int(nodes["child0"][ni]), int(nodes["child1"][ni])):
+            if ch >= 0:
+                order_stack.append(ch)
+    assert len(set(visit)) == len(visit)
+
+    def leaf_bounds(ref):
+        code = (~ref) & 0xFFFFFFFF
+        first, count = code >> 3, (code & 7) + 1
+        assert 1 <= count <= 8 and first + count <= n
+        covered[first:first + count] += 1
+        idx = order[first:first + count]
+        return tri_lo[idx].min(0), tri_hi[idx].max(0)
+
+    for ni in reversed(visit):
+        nd = nodes[ni]
+        res = []
+        for ch, lo, hi in ((int(nd["child0"]), nd["lo0"], nd["hi0"]), (int(nd["child1"]), nd["lo1"], nd["hi1"])):
+            l, h = leaf_bounds(ch) if ch < 0 else bounds[ch]
+            assert (lo <= l - pad_min).all() and (hi >= h + pad_min).all()
+            res.append((l, h))
+        bounds[ni] = (np.minimum(res[0][0], res[1][0]), np.maximum(res[0][1], res[1][1]))
+    assert (covered == 1).all()
+    assert sorted(order.tolist()) == list(range(n))
+
+
+@pytest.mark.parametrize("k,max_leaf", [(1, 4), (6, 2), (20, 4)])
+def test_gpu_lbvh_builder(dev, pt, ob, cornell, k, max_leaf):
+    """BVH built on the device: valid tree, hits == the reference's brute-force loop, renders == oracle on that tree."""
+    tris, mats = cornell
+    scene_tris = tris if k == 1 else pt.tessellate(tris, k)
+    p1, ea, eb = pt.light_from_quad(tris, 5)
+    sc = dev.scene(scene_tris, mats, pt.bvh_params(max_leaf=max_leaf), gpu_build=True)
+    info = sc.info()
+    assert info["n_nodes"] == len(scene_tris) - 1 and info["smem_nodes"] == 1 and 1 <= info["depth"] <= 64
+    nodes, order = sc.bvh()
+    _check_tree(nodes, order, scene_tris, pad_min=5e-4)
+    # deterministic: a second build gives the same bytes
+    sc2 = dev.scene(scene_tris, mats, pt.bvh_params(max_leaf=max_leaf), gpu_build=True)
+    n2, o2 = sc2.bvh()
+    assert np.array_equal(o2, order)
+    live = np.zeros(len(nodes), bool)
+    st = [0]
+    while st:
+        i = st.pop(); live[i] = True
+        st += [int(c) for c in (nodes["child0"][i], nodes["child1"][i]) if c >= 0]
+    assert nodes[live].tobytes() == n2[live].tobytes()
+    sc2.close()
+    o, d = _rays(30_000, 17)
+    g = dev.trace(sc, o, d, np.float32(1e20), accel=pt.ACCEL_BVH)
+    r = ob.trace(scene_tris, o, d, np.float32(1e20), bvh=None)
+    for f in ("tri", "t", "u", "v"):
+        np.testing.assert_array_equal(bits(g[f]), bits(r[f]))
+    bvh, _keep = ob.make_bvh(nodes, order)
+    gv = ob.trace(scene_tris, o, d, np.float32(1e20), bvh=bvh)
+    np.testing.assert_array_equal(g["visits"], gv["visits"])
+    w, h = 72, 56
+    for mode, integ in ((1, pt.INTEGRATOR_MEGAKERNEL), (3, pt.INTEGRATOR_MEGAKERNEL), (3, pt.INTEGRATOR_WAVEFRONT), (2, pt.INTEGRATOR_WAVEFRONT)):
+        prm = pt.default_params(width=w, height=h, n_frames=2, mode=mode, accum=pt.ACCUM_LINEAR, max_depth=5, collect_stats=1,
+                                integrator=integ, light_p1=p1, light_ea=ea, light_eb=eb)
+        frame, stats = dev.buffer(w * h * 16), dev.buffer(w * h * 32)
+        ctr = dev.render(sc, prm, frame, stats, want_counters=True)
+        fb, stt = frame.read(np.float32).reshape(-1, 4), stats.read(pt.STATS_DTYPE)
+        frame.close(); stats.close()
+        oprm = ob.default_params(w, h, n_frames=2, mode=mode, accum=1, max_depth=5, use_bvh=1, light_p1=p1, light_ea=ea, light_eb=eb)
+        ofb, ost, octr = ob.render(oprm, scene_tris, mats, bvh=bvh, want_stats=True)
+        np.testing.assert_array_equal(bits(fb), bits(ofb))
+        assert stt.tobytes() == ost.tobytes() and ctr["nodes"] == octr["nodes"]
+    sc.close()
