@@ -494,6 +494,9 @@ static ptd::SceneDev scene_dev(const ptb_scene* s) {
     d.smem_nodes = s->small ? s->bfs_nodes : (s->bfs_nodes < cap ? s->bfs_nodes : cap);
     d.small = s->small ? 1 : 0;
     d.stack_depth = s->depth + 1;
+    // scenes traversed from L2/HBM keep the stack in local memory: shared memory then holds only the node
+    // prefix and occupancy is bounded by registers (C5: +2.4 %); tune[2]=2 forces the shared-memory stack
+    d.lstack = (!s->small && s->dev->tune[2] != 2 && s->depth + 1 <= PTD_LSTACK_ENTRIES) ? 1 : 0;
     return d;
 }
 

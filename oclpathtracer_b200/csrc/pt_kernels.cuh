@@ -85,12 +85,13 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
     c.g_tris = TRIS_BVH ? sc.tris : sc.tris_orig;
     c.g_mats = sc.mats;
     c.stride_bytes = blockDim.x * 4u;
-    const uint32_t stack_bytes = NODES ? (uint32_t)sc.stack_depth * blockDim.x * 4u : 0u;
+    const uint32_t stack_bytes = (NODES && !sc.lstack) ? (uint32_t)sc.stack_depth * blockDim.x * 4u : 0u;
     c.s_stack_ref = smem_u32(s_stack) + threadIdx.x * 4u;
     c.s_stack_tn = c.s_stack_ref + stack_bytes;
     c.s_scratch = c.s_stack_tn + stack_bytes;
     c.smem_nodes = sc.smem_nodes;
     c.n_tris = sc.n_tris;
+    c.lstack = nullptr;
     return c;
 }
 
@@ -99,7 +100,7 @@ static inline size_t scene_smem_bytes(const SceneDev& sc, bool bvh, bool small, 
     size_t b = 16;
     if (bvh) b += (size_t)sc.smem_nodes * 64;
     if (small) b += (size_t)sc.n_tris * 48 + (size_t)sc.n_mats * 32;
-    if (bvh) b += (size_t)sc.stack_depth * block * 8;
+    if (bvh && !sc.lstack) b += (size_t)sc.stack_depth * block * 8;
     return b + scratch_per_thread * block;
 }
 
@@ -313,7 +314,9 @@ PTD_FI V3 sample_direct(const Ctx& c, const RenderArgs& a, Ray r, uint32_t& seed
 template <int MODE, bool BVH, bool SMALL, bool STATS>
 __global__ void __launch_bounds__(128) k_mega(const SceneDev sc, const RenderArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    uint2 lstack_mem[PTD_LSTACK_ENTRIES];
+    if (BVH && !SMALL && sc.lstack) c.lstack = lstack_mem;
 
     const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)a.frames_in_batch * a.n_local;
@@ -361,7 +364,9 @@ template <bool BVH, bool SMALL, bool STATS>
 __global__ void __launch_bounds__(128) k_mega_path_regen(const SceneDev sc, const RenderArgs a,
                                                          unsigned long long* work_counter) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    uint2 lstack_mem[PTD_LSTACK_ENTRIES];
+    if (BVH && !SMALL && sc.lstack) c.lstack = lstack_mem;
     const long long total = (long long)a.frames_in_batch * a.n_local;
     const unsigned lane = threadIdx.x & 31u;
     RayCount rc{0u, 0u};
@@ -497,7 +502,9 @@ struct TraceArgs {
 template <bool BVH, bool ANY, bool SMALL>
 __global__ void __launch_bounds__(128) k_trace(const SceneDev sc, const TraceArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    uint2 lstack_mem[PTD_LSTACK_ENTRIES];
+    if (BVH && !SMALL && sc.lstack) c.lstack = lstack_mem;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_rays) return;
     const V3 o = mk(a.o[3 * i], a.o[3 * i + 1], a.o[3 * i + 2]);

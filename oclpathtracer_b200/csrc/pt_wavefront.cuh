@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(128) wf_extend(const SceneDev sc, const WfBuff
     const unsigned int n = w.counts[depth];
     if (blockIdx.x * blockDim.x >= n) return;
     extern __shared__ __align__(16) unsigned char smem[];
-    const Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    uint2 lstack_mem[PTD_LSTACK_ENTRIES];
+    if (BVH && !SMALL && sc.lstack) c.lstack = lstack_mem;
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nrays = 0;
     QueryStats qs{0u, 0u};
@@ -239,7 +241,9 @@ __global__ void __launch_bounds__(128) wf_extend_p(const SceneDev sc, const WfBu
     const unsigned int n = w.counts[depth];
     if (blockIdx.x * blockDim.x >= n) return;
     extern __shared__ __align__(16) unsigned char smem[];
-    const Ctx c = stage_scene<true, SMALL>(sc, smem);
+    Ctx c = stage_scene<true, SMALL>(sc, smem);
+    uint2 lstack_mem[PTD_LSTACK_ENTRIES];
+    if (!SMALL && sc.lstack) c.lstack = lstack_mem;
     ExtendStore<SMALL, STATS> io;
     io.qo = w.q_o[qi]; io.qd = w.q_d[qi]; io.hit = w.hit; io.slot_stats = w.slot_stats; io.depth = depth; io.slot = 0;
     io.c = &c;
@@ -304,7 +308,9 @@ __global__ void __launch_bounds__(128) wf_shadow_p(const SceneDev sc, const Rend
                                                    const unsigned int n_rays, unsigned int* work,
                                                    unsigned long long* counters, const int refill_thr) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const Ctx c = stage_scene<true, SMALL>(sc, smem);
+    Ctx c = stage_scene<true, SMALL>(sc, smem);
+    uint2 lstack_mem[PTD_LSTACK_ENTRIES];
+    if (!SMALL && sc.lstack) c.lstack = lstack_mem;
     ShadowIO<MODE, STATS> io;
     io.a = &a; io.w = &w; io.P = (long long)a.frames_in_batch * a.n_local;
     uint32_t nrays = 0;
@@ -514,7 +520,9 @@ template <int MODE, bool BVH, bool SMALL, bool STATS>
 __global__ void __launch_bounds__(128) wf_shadow(const SceneDev sc, const RenderArgs a, const WfBuffers w,
                                                  const long long n_rays, unsigned long long* counters) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    Ctx c = stage_scene<BVH, SMALL>(sc, smem);
+    uint2 lstack_mem[PTD_LSTACK_ENTRIES];
+    if (BVH && !SMALL && sc.lstack) c.lstack = lstack_mem;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long P = (long long)a.frames_in_batch * a.n_local;
     uint32_t nrays = 0;

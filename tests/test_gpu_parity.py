@@ -249,8 +249,18 @@ def test_single_triangle_and_miss_paths(dev, pt, ob, cornell):
             assert (st["tri"] == -1).any() and (st["tri"] == 0).any()
 
 
-def test_tessellated_scene_global_memory_path(dev, pt, ob, cornell):
-    """k=12 -> 5184 triangles: nodes beyond the shared-memory prefix and triangles come from global memory."""
+@pytest.mark.parametrize("stack", ["local", "shared"])
+def test_tessellated_scene_global_memory_path(dev, pt, ob, cornell, stack):
+    """k=12 -> 5184 triangles: nodes beyond the shared-memory prefix and triangles come from global memory;
+    the traversal stack lives in local memory (default) or in shared memory (tune[2]=2)."""
+    dev.set_tuning(2, 2 if stack == "shared" else 0)
+    try:
+        _tessellated_body(dev, pt, ob, cornell)
+    finally:
+        dev.set_tuning(2, 0)
+
+
+def _tessellated_body(dev, pt, ob, cornell):
     tris, mats = cornell
     big = pt.tessellate(tris, 12)
     p1, ea, eb = pt.light_from_quad(tris, 5)
@@ -258,6 +268,7 @@ def test_tessellated_scene_global_memory_path(dev, pt, ob, cornell):
     sc = dev.scene(big, mats, bp)
     info = sc.info()
     assert info["n_nodes"] > info["smem_nodes"] == 128
+    dev.set_tuning(4, 128)  # stage the whole 128-node prefix (default cap is 64)
     nodes, order = sc.bvh()
     bvh, _keep = ob.make_bvh(nodes, order)
     w, h = 64, 64
@@ -280,6 +291,7 @@ def test_tessellated_scene_global_memory_path(dev, pt, ob, cornell):
     r = ob.trace(big, o, d, np.float32(1e20), bvh=None)
     for f in ("tri", "t", "u", "v"):
         np.testing.assert_array_equal(bits(g[f]), bits(r[f]))
+    dev.set_tuning(4, 0)
     sc.close()
 
 
