@@ -54,18 +54,21 @@ typedef struct ptb_triangle {
 
 /* One internal BVH node = 4 x 128-bit words, 64-byte aligned.  It holds the
  * (padded) boxes of BOTH children, so one coalesced 64-byte fetch decides both
- * descents.  Child reference: >= 0 internal node index; < 0 leaf, decoded as
+ * descents.  Boxes are stored as CENTRE and HALF-EXTENT (box = [c - e, c + e]):
+ * the slab test is then three FMAs per axis and needs no per-axis min/max
+ * (t_centre = c*invd - o*invd, t_near = t_centre - e*|invd|, t_far = t_centre + e*|invd|).
+ * Child reference: >= 0 internal node index; < 0 leaf, decoded as
  * first = (~ref) >> 3, count = ((~ref) & 7) + 1 into the ordered triangle
  * array; PTB_BVH_EMPTY = no child.                                            */
 typedef struct ptb_bvh_node {
-    float lo0[3];
-    int32_t child0; /* word 0: child-0 box min, child-0 ref */
-    float hi0[3];
-    int32_t child1; /* word 1: child-0 box max, child-1 ref */
-    float lo1[3];
-    int32_t pad0; /* word 2: child-1 box min */
-    float hi1[3];
-    int32_t pad1; /* word 3: child-1 box max */
+    float c0[3];
+    int32_t child0; /* word 0: child-0 box centre, child-0 ref */
+    float e0[3];
+    int32_t child1; /* word 1: child-0 box half-extent, child-1 ref */
+    float c1[3];
+    int32_t pad0; /* word 2: child-1 box centre */
+    float e1[3];
+    int32_t pad1; /* word 3: child-1 box half-extent */
 } ptb_bvh_node;
 
 #define PTB_BVH_EMPTY 0x7fffffff

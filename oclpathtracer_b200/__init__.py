@@ -26,8 +26,8 @@ MATERIAL_DTYPE = np.dtype(
 )
 NODE_DTYPE = np.dtype(
     [
-        ("lo0", "<f4", 3), ("child0", "<i4"), ("hi0", "<f4", 3), ("child1", "<i4"),
-        ("lo1", "<f4", 3), ("pad0", "<i4"), ("hi1", "<f4", 3), ("pad1", "<i4"),
+        ("c0", "<f4", 3), ("child0", "<i4"), ("e0", "<f4", 3), ("child1", "<i4"),
+        ("c1", "<f4", 3), ("pad0", "<i4"), ("e1", "<f4", 3), ("pad1", "<i4"),
     ]
 )
 STATS_DTYPE = np.dtype(

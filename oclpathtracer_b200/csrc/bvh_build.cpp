@@ -143,6 +143,13 @@ struct Builder {
     }
 };
 
+// [lo, hi] -> centre / half-extent, widened by two ulps so that [c - e, c + e] still contains [lo, hi]
+void centre_extent(float lo, float hi, float* c, float* e) {
+    *c = 0.5f * lo + 0.5f * hi;
+    const float h = 0.5f * hi - 0.5f * lo;
+    *e = h + 2.4e-7f * (std::fabs(*c) + h);
+}
+
 void edge_tri(const ptb_triangle& t, int32_t index, ptb_bvh_tri* o) {
     const float* p1 = &t.p1.x;
     const float* p2 = &t.p2.x;
@@ -242,8 +249,8 @@ int build_bvh(const ptb_triangle* tris, int n_tris, const ptb_bvh_params& params
         d.child0 = t.child[0] >= 0 ? new_of[t.child[0]] : t.child[0];
         d.child1 = t.child[1] >= 0 ? new_of[t.child[1]] : t.child[1];
         for (int a = 0; a < 3; ++a) {
-            d.lo0[a] = t.box[0].lo[a] - pad; d.hi0[a] = t.box[0].hi[a] + pad;
-            d.lo1[a] = t.box[1].lo[a] - pad; d.hi1[a] = t.box[1].hi[a] + pad;
+            centre_extent(t.box[0].lo[a] - pad, t.box[0].hi[a] + pad, &d.c0[a], &d.e0[a]);
+            centre_extent(t.box[1].lo[a] - pad, t.box[1].hi[a] + pad, &d.c1[a], &d.e1[a]);
         }
         d.pad0 = d.pad1 = 0;
     }

@@ -161,11 +161,19 @@ __global__ void __launch_bounds__(256) k_lbvh_finish(const ptb_triangle* tris, c
     const float pad = fmaxf(pad_rel, 0.0f) * sqrtf(dx * dx + dy * dy + dz * dz);
     if (i < n - 1) {
         float4* nd = nodes + 4 * (size_t)i;
+        // padded [lo, hi] of each child -> centre / half-extent widened by two ulps (same rule as the host builder)
         float4 a = nd[0], b = nd[1], c = nd[2], d = nd[3];
-        a.x -= pad; a.y -= pad; a.z -= pad; b.x += pad; b.y += pad; b.z += pad;
-        c.x -= pad; c.y -= pad; c.z -= pad; d.x += pad; d.y += pad; d.z += pad;
-        c.w = 0.f; d.w = 0.f;
-        nd[0] = a; nd[1] = b; nd[2] = c; nd[3] = d;
+        auto ce = [pad](float lo, float hi, float& cc, float& ee) {
+            lo -= pad; hi += pad;
+            cc = 0.5f * lo + 0.5f * hi;
+            const float h = 0.5f * hi - 0.5f * lo;
+            ee = h + 2.4e-7f * (fabsf(cc) + h);
+        };
+        float4 o0 = a, o1 = b, o2 = c, o3 = d;
+        ce(a.x, b.x, o0.x, o1.x); ce(a.y, b.y, o0.y, o1.y); ce(a.z, b.z, o0.z, o1.z);
+        ce(c.x, d.x, o2.x, o3.x); ce(c.y, d.y, o2.y, o3.y); ce(c.z, d.z, o2.z, o3.z);
+        o2.w = 0.f; o3.w = 0.f;
+        nd[0] = o0; nd[1] = o1; nd[2] = o2; nd[3] = o3;
     }
     if (i < n) {
         const int tri = (int)(keys[i] & 0xffffffffull);

@@ -23,7 +23,7 @@
  *       exactly; measured max error vs libm double: sin/cos <= 1 ulp on [0, 2pi],
  *       pow correctly rounded to < 0.5000001 ulp (double intermediate).
  *   N4. BUILD-DEFINED BVH slab test uses explicit fmaf and fminf/fmaxf (below,
- *       bvh_slab); everything pinned by the reference stays unfused.
+ *       bvh_slab: centre / half-extent boxes); everything pinned by the reference stays unfused.
  * ---------------------------------------------------------------------------
  */
 #include "oracle_pt.h"
@@ -402,13 +402,15 @@ static inline float safe_rcp(float d) {
     if (fabsf(d) > 1e-20f) return 1.0f / d;
     return signbit(d) ? -1e20f : 1e20f;
 }
-static inline int bvh_slab(const float lo[3], const float hi[3], const float invd[3], const float ood[3],
+/* box = [c - e, c + e]; per axis t_c = c*invd - o*invd, t_near = t_c - e*|invd|, t_far = t_c + e*|invd| */
+static inline int bvh_slab(const float c[3], const float e[3], const float invd[3], const float ood[3],
                            float best_t, float* tn_out) {
-    float t0x = fmaf(lo[0], invd[0], -ood[0]), t1x = fmaf(hi[0], invd[0], -ood[0]);
-    float t0y = fmaf(lo[1], invd[1], -ood[1]), t1y = fmaf(hi[1], invd[1], -ood[1]);
-    float t0z = fmaf(lo[2], invd[2], -ood[2]), t1z = fmaf(hi[2], invd[2], -ood[2]);
-    float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-    float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best_t));
+    float tcx = fmaf(c[0], invd[0], -ood[0]), tcy = fmaf(c[1], invd[1], -ood[1]), tcz = fmaf(c[2], invd[2], -ood[2]);
+    float ax = fabsf(invd[0]), ay = fabsf(invd[1]), az = fabsf(invd[2]);
+    float nx = fmaf(-e[0], ax, tcx), ny = fmaf(-e[1], ay, tcy), nz = fmaf(-e[2], az, tcz);
+    float fx = fmaf(e[0], ax, tcx), fy = fmaf(e[1], ay, tcy), fz = fmaf(e[2], az, tcz);
+    float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
+    float tf = fminf(fminf(fx, fy), fminf(fz, best_t));
     *tn_out = tn;
     return tn <= tf;
 }
@@ -445,8 +447,8 @@ static int bvh_query(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, f
             (*visits)++;
             c->nodes++;
             float tn0, tn1;
-            int h0 = nd->child0 != 0x7fffffff && bvh_slab(nd->lo0, nd->hi0, invd, ood, best_t, &tn0);
-            int h1 = nd->child1 != 0x7fffffff && bvh_slab(nd->lo1, nd->hi1, invd, ood, best_t, &tn1);
+            int h0 = nd->child0 != 0x7fffffff && bvh_slab(nd->c0, nd->e0, invd, ood, best_t, &tn0);
+            int h1 = nd->child1 != 0x7fffffff && bvh_slab(nd->c1, nd->e1, invd, ood, best_t, &tn1);
             if (h0 && h1) {
                 if (tn1 < tn0) {
                     stack_ref[sp] = nd->child0; stack_tn[sp] = tn0; sp++;

@@ -56,13 +56,13 @@ typedef struct ora_triangle {
  * host builder, validated structurally by tests): same byte layout as
  * include/SharedHeader.h:ptb_bvh_node.                                         */
 typedef struct ora_bvh_node {
-    float lo0[3];
+    float c0[3]; /* child-0 box centre      */
     int32_t child0;
-    float hi0[3];
+    float e0[3]; /* child-0 box half-extent */
     int32_t child1;
-    float lo1[3];
+    float c1[3];
     int32_t pad0;
-    float hi1[3];
+    float e1[3];
     int32_t pad1;
 } ora_bvh_node;
 

@@ -537,9 +537,10 @@ def _check_tree(nodes, order, tris, pad_min):
     for ni in reversed(visit):
         nd = nodes[ni]
         res = []
-        for ch, lo, hi in ((int(nd["child0"]), nd["lo0"], nd["hi0"]), (int(nd["child1"]), nd["lo1"], nd["hi1"])):
+        for ch, c, e in ((int(nd["child0"]), nd["c0"], nd["e0"]), (int(nd["child1"]), nd["c1"], nd["e1"])):
             l, h = leaf_bounds(ch) if ch < 0 else bounds[ch]
-            assert (lo <= l - pad_min).all() and (hi >= h + pad_min).all()
+            c, e = c.astype(np.float64), e.astype(np.float64)
+            assert (c - e <= l - pad_min).all() and (c + e >= h + pad_min).all()
             res.append((l, h))
         bounds[ni] = (np.minimum(res[0][0], res[1][0]), np.maximum(res[0][1], res[1][1]))
     assert (covered == 1).all()

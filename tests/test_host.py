@@ -78,8 +78,9 @@ def _validate_bvh(pt, tris, b, pad_min=0.0):
         nd = nodes[ref]
         l0, h0 = bounds(int(nd["child0"]))
         l1, h1 = bounds(int(nd["child1"]))
-        assert (nd["lo0"] <= l0 - pad_min).all() and (nd["hi0"] >= h0 + pad_min).all()
-        assert (nd["lo1"] <= l1 - pad_min).all() and (nd["hi1"] >= h1 + pad_min).all()
+        for (l, h, c, e) in ((l0, h0, nd["c0"], nd["e0"]), (l1, h1, nd["c1"], nd["e1"])):  # box = [c - e, c + e]
+            c, e = c.astype(np.float64), e.astype(np.float64)
+            assert (e > 0).all() and (c - e <= l - pad_min).all() and (c + e >= h + pad_min).all()
         return np.minimum(l0, l1), np.maximum(h0, h1)
 
     import sys
