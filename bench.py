@@ -68,7 +68,7 @@ class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
@@ -90,8 +90,15 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+        import datetime
+        for line in self.proc.stdout:  # the pipe is block-buffered: use nvidia-smi's own timestamp, not the arrival time
+            cols = [c.strip() for c in line.split(",")]
+            ts = time.time()
+            try:
+                ts = datetime.datetime.strptime(cols[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except (IndexError, ValueError):
+                pass
+            self.rows.append((ts, cols))
 
     def stop(self):
         if not self.proc:
