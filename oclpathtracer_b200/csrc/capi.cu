@@ -197,6 +197,7 @@ extern "C" int ptb_device_destroy(ptb_device* dev) {
     if (!dev) return PTB_OK;
     set_device(dev);
     cudaStreamSynchronize(dev->stream);
+    if (dev->copy_stream) cudaStreamSynchronize(dev->copy_stream);
     if (dev->host_scene) ptb_scene_destroy(dev->host_scene);
     for (auto& sl : dev->slots) {
         if (sl.frame) ptb_buffer_destroy(sl.frame);
