@@ -55,6 +55,8 @@ int ptb_device_sync(ptb_device* dev);
 /* Device::getDeviceVersion(char[128])  Adl/Adl.h:164 (names the PPM) */
 int ptb_device_name(ptb_device* dev, char out[128]);
 int ptb_device_sm_count(ptb_device* dev, int* sm_count);
+/* Device::getMaxAllocationSize / memory accounting  Adl/Adl.h:168-170,173 */
+int ptb_device_memory(ptb_device* dev, size_t* free_bytes, size_t* total_bytes);
 void* ptb_device_stream(ptb_device* dev);
 
 /* ---- buffers: adl::Buffer<T>  Adl/Adl.h:203-265, Adl/Adl.inl:145-253 ------------

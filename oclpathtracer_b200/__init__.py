@@ -79,7 +79,7 @@ _lib = None
 # every symbol include/ptb200.h declares
 EXPORTS = [
     "ptb_last_error", "ptb_version", "ptb_device_count", "ptb_device_create", "ptb_device_create_on_stream",
-    "ptb_device_destroy", "ptb_device_sync", "ptb_device_name", "ptb_device_sm_count", "ptb_device_stream",
+    "ptb_device_destroy", "ptb_device_sync", "ptb_device_name", "ptb_device_sm_count", "ptb_device_memory", "ptb_device_stream",
     "ptb_buffer_create", "ptb_buffer_wrap", "ptb_buffer_destroy", "ptb_buffer_write", "ptb_buffer_read",
     "ptb_buffer_map", "ptb_buffer_unmap", "ptb_buffer_clear", "ptb_buffer_device_ptr", "ptb_buffer_size",
     "ptb_kernel_get", "ptb_kernel_set_int", "ptb_launch1d", "ptb_launch_serialize", "ptb_launch_deserialize", "ptb_load_model", "ptb_tessellate",
@@ -123,6 +123,7 @@ def lib():
         L.ptb_device_name.argtypes = [C.c_void_p, C.c_char_p]
         L.ptb_device_sm_count.argtypes = [C.c_void_p, C.c_void_p]
         L.ptb_device_stream.argtypes = [C.c_void_p]
+        L.ptb_device_memory.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ptb_bvh_build_host.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
         L.ptb_scene_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptb_scene_create_gpu.argtypes = L.ptb_scene_create.argtypes

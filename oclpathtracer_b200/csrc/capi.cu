@@ -237,6 +237,15 @@ extern "C" int ptb_device_sm_count(ptb_device* dev, int* sm) {
     *sm = dev->prop.multiProcessorCount;
     return PTB_OK;
 }
+extern "C" int ptb_device_memory(ptb_device* dev, size_t* free_bytes, size_t* total_bytes) {
+    if (!dev) return fail(PTB_E_INVALID, "ptb_device_memory: null device");
+    if (set_device(dev)) return PTB_E_CUDA;
+    size_t f = 0, t = 0;
+    CU_TRY(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return PTB_OK;
+}
 extern "C" void* ptb_device_stream(ptb_device* dev) { return dev ? (void*)dev->stream : nullptr; }
 
 // ---- buffers --------------------------------------------------------------------------------------

@@ -49,6 +49,13 @@ class Device {
     }
     void getDeviceVersion(char nameOut[128]) const { ptb_device_name(m_dev, nameOut); }
     void getDeviceName(char nameOut[128]) const { ptb_device_name(m_dev, nameOut); }
+    void getBoardName(char nameOut[128]) const { ptb_device_name(m_dev, nameOut); }
+    void getDeviceVendor(char nameOut[128]) const { std::strncpy(nameOut, "NVIDIA Corporation", 127); nameOut[127] = 0; }
+    adlu64 getMaxAllocationSize() const {
+        size_t f = 0, t = 0;
+        ptb_device_memory(m_dev, &f, &t);
+        return (adlu64)f;
+    }
     DeviceType m_type;
     ptb_device* m_dev;
 

@@ -590,3 +590,14 @@ def test_gpu_lbvh_builder(dev, pt, ob, cornell, k, max_leaf):
         np.testing.assert_array_equal(bits(fb), bits(ofb))
         assert stt.tobytes() == ost.tobytes() and ctr["nodes"] == octr["nodes"]
     sc.close()
+
+
+def test_reference_device_tests_over_shim():
+    """host/adl_tests.cpp: the reference's DeviceTest cases (test/main.cpp:53-152 + RayCast) over the ADL-shaped shim."""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oclpathtracer_b200", "host", "adl_tests")
+    subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    r = subprocess.run([exe, SCENE], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("[       OK ]") == 7
