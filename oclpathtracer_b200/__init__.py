@@ -27,7 +27,9 @@ MATERIAL_DTYPE = np.dtype(
 NODE_DTYPE = np.dtype(
     [
         ("c0", "<f4", 3), ("child0", "<i4"), ("e0", "<f4", 3), ("child1", "<i4"),
-        ("c1", "<f4", 3), ("pad0", "<i4"), ("e1", "<f4", 3), ("pad1", "<i4"),
+        ("c1", "<f4", 3), ("child2", "<i4"), ("e1", "<f4", 3), ("child3", "<i4"),
+        ("c2", "<f4", 3), ("pad0", "<i4"), ("e2", "<f4", 3), ("pad1", "<i4"),
+        ("c3", "<f4", 3), ("pad2", "<i4"), ("e3", "<f4", 3), ("pad3", "<i4"),
     ]
 )
 STATS_DTYPE = np.dtype(
@@ -234,7 +236,7 @@ def build_bvh_host(tris, params=None):
                                 C.byref(sn)))
     try:
         res = {
-            "nodes": np.frombuffer(C.string_at(nodes, nn.value * 64), NODE_DTYPE).copy(),
+            "nodes": np.frombuffer(C.string_at(nodes, nn.value * 128), NODE_DTYPE).copy(),
             "tri_order": np.frombuffer(C.string_at(order, len(tris) * 4), np.int32).copy(),
             "ordered_tris": np.frombuffer(C.string_at(otris, len(tris) * 48), BVH_TRI_DTYPE).copy(),
             "depth": depth.value, "smem_nodes": sn.value,

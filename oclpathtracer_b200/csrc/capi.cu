@@ -372,7 +372,7 @@ extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n
         m[2 * i + 1] = make_float4(mats[i].emissive.x, mats[i].emissive.y, mats[i].emissive.z, tbits);
     }
     s->n_nodes = int(s->bvh.nodes.size()); s->depth = s->bvh.depth; s->bfs_nodes = s->bvh.smem_nodes;
-    const size_t staged = s->bvh.nodes.size() * 64 + size_t(n_tris) * 48 + size_t(n_mats) * 32;
+    const size_t staged = s->bvh.nodes.size() * sizeof(ptb_bvh_node) + size_t(n_tris) * 48 + size_t(n_mats) * 32;
     s->small = staged <= 32 * 1024 && int(s->bvh.nodes.size()) == s->bvh.smem_nodes;
     if (set_device(dev)) { delete s; return PTB_E_CUDA; }
     auto up = [&](float4** d, const void* h, size_t bytes) -> int {
@@ -380,7 +380,7 @@ extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n
         CU_TRY(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, dev->stream));
         return PTB_OK;
     };
-    if ((rc = up(&s->d_nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * 64)) ||
+    if ((rc = up(&s->d_nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptb_bvh_node))) ||
         (rc = up(&s->d_tris, s->bvh.tris.data(), s->bvh.tris.size() * 48)) ||
         (rc = up(&s->d_tris_orig, orig.data(), orig.size() * 48)) || (rc = up(&s->d_mats, m.data(), m.size() * 16))) {
         ptb_scene_destroy(s);
@@ -483,7 +483,7 @@ extern "C" int ptb_scene_copy_bvh(ptb_scene* s, ptb_bvh_node* nodes, int32_t* tr
         if (set_device(s->dev)) return PTB_E_CUDA;
         s->bvh.nodes.resize(size_t(s->n_nodes));
         s->bvh.tri_order.resize(size_t(s->n_tris));
-        CU_TRY(cudaMemcpyAsync(s->bvh.nodes.data(), s->d_nodes, size_t(s->n_nodes) * 64, cudaMemcpyDeviceToHost, s->dev->stream));
+        CU_TRY(cudaMemcpyAsync(s->bvh.nodes.data(), s->d_nodes, size_t(s->n_nodes) * sizeof(ptb_bvh_node), cudaMemcpyDeviceToHost, s->dev->stream));
         CU_TRY(cudaMemcpyAsync(s->bvh.tri_order.data(), s->d_order, size_t(s->n_tris) * 4, cudaMemcpyDeviceToHost, s->dev->stream));
         CU_TRY(cudaStreamSynchronize(s->dev->stream));
         s->host_copy_valid = true;
@@ -497,16 +497,16 @@ static ptd::SceneDev scene_dev(const ptb_scene* s) {
     ptd::SceneDev d;
     d.nodes = s->d_nodes; d.tris = s->d_tris; d.tris_orig = s->d_tris_orig; d.mats = s->d_mats;
     d.n_nodes = s->n_nodes; d.n_tris = s->n_tris; d.n_mats = s->n_mats;
-    // Large scenes stage only the top of the tree: a 64-node (4 KB) prefix keeps >= 6 CTAs per SM
-    // resident next to the traversal stack (measured on the 2M-triangle scene: 1024 nodes 0.83,
-    // 256 nodes 1.81, 64 nodes 2.28 Grays/s).
-    const int cap = s->dev->tune[4] > 0 ? s->dev->tune[4] : 64;
+    // Large scenes stage only the top of the tree: a 32-node (4 KB) prefix keeps occupancy high
+    // (measured on the 2M-triangle scene with binary 64-byte nodes: 1024 nodes 0.83, 256 nodes 1.81,
+    // 64 nodes 2.28 Grays/s).
+    const int cap = s->dev->tune[4] > 0 ? s->dev->tune[4] : 32;
     d.smem_nodes = s->small ? s->bfs_nodes : (s->bfs_nodes < cap ? s->bfs_nodes : cap);
     d.small = s->small ? 1 : 0;
-    d.stack_depth = s->depth + 1;
+    d.stack_depth = 3 * s->depth + 1;  // a 4-wide visit defers up to three children
     // scenes traversed from L2/HBM keep the stack in local memory: shared memory then holds only the node
     // prefix and occupancy is bounded by registers (C5: +2.4 %); tune[2]=2 forces the shared-memory stack
-    d.lstack = (!s->small && s->dev->tune[2] != 2 && s->depth + 1 <= PTD_LSTACK_ENTRIES) ? 1 : 0;
+    d.lstack = (!s->small && s->dev->tune[2] != 2 && 3 * s->depth + 1 <= PTD_LSTACK_ENTRIES) ? 1 : 0;
     return d;
 }
 

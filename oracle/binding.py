@@ -27,7 +27,9 @@ MATERIAL_DTYPE = np.dtype(
 NODE_DTYPE = np.dtype(
     [
         ("c0", "<f4", 3), ("child0", "<i4"), ("e0", "<f4", 3), ("child1", "<i4"),
-        ("c1", "<f4", 3), ("pad0", "<i4"), ("e1", "<f4", 3), ("pad1", "<i4"),
+        ("c1", "<f4", 3), ("child2", "<i4"), ("e1", "<f4", 3), ("child3", "<i4"),
+        ("c2", "<f4", 3), ("pad0", "<i4"), ("e2", "<f4", 3), ("pad1", "<i4"),
+        ("c3", "<f4", 3), ("pad2", "<i4"), ("e3", "<f4", 3), ("pad3", "<i4"),
     ]
 )
 STATS_DTYPE = np.dtype(
@@ -37,7 +39,7 @@ STATS_DTYPE = np.dtype(
     ]
 )
 assert TRIANGLE_DTYPE.itemsize == 64 and MATERIAL_DTYPE.itemsize == 64
-assert NODE_DTYPE.itemsize == 64 and STATS_DTYPE.itemsize == 32
+assert NODE_DTYPE.itemsize == 128 and STATS_DTYPE.itemsize == 32
 
 
 class Bvh(C.Structure):

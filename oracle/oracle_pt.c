@@ -415,18 +415,20 @@ static inline int bvh_slab(const float c[3], const float e[3], const float invd[
     return tn <= tf;
 }
 
-#define ORA_STACK 96
 
-/* BUILD-DEFINED traversal (the specification of node-visit counts):
- *  - `cur` >= 0: fetch the node (visits++), slab-test both child boxes against
- *    [0, best_t]; both hit -> descend into the nearer (child 1 only if
- *    tn1 < tn0), push the other with its entry distance; one hit -> descend.
- *  - `cur` < 0: leaf; test its triangles in stored order.  Closest: accept when
- *    t < best_t, or t == best_t and the triangle's index is lower than the
- *    current winner's (== the reference's "first index wins").  Any: return at
- *    the first triangle with 0 < t < tmax.
- *  - pop: entries whose stored entry distance exceeds best_t are discarded
- *    unvisited.                                                               */
+/* BUILD-DEFINED traversal over the 4-wide tree (the specification of node-visit counts):
+ *  - `cur` >= 0: fetch the node (visits++), slab-test its four child boxes against [0, best_t].
+ *      closest-hit: the hit children are ordered by the key (bits of their entry distance tn with the two
+ *        low mantissa bits replaced by the slot index) ascending; descend into the first, push the others
+ *        so that the nearer pops first, each with its truncated entry distance (key & ~3);
+ *      any-hit: descend into the hit child with the lowest slot index, push the others so that the lower
+ *        slot pops first.
+ *  - `cur` < 0: leaf; test its triangles in stored order.  Closest: accept when t < best_t, or t == best_t
+ *    and the triangle's index is lower than the current winner's (== the reference's "first index wins").
+ *    Any: return at the first triangle with 0 < t < tmax.
+ *  - pop: closest-hit entries whose stored entry distance exceeds best_t are discarded unvisited.         */
+#define ORA_STACK 256
+
 static int bvh_query(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, float tmax, int any_hit, qhit* h,
                      uint32_t* visits, qctr* c) {
     float invd[3] = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
@@ -440,30 +442,44 @@ static int bvh_query(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, f
     int32_t cur = 0;
     if (any_hit) c->any++; else c->closest++;
     for (;;) {
-        if (cur == 0x7fffffff) {
-            /* empty child: nothing */
-        } else if (cur >= 0) {
+        int descend = 0;
+        if (cur >= 0) {
             const ora_bvh_node* nd = &bvh->nodes[cur];
             (*visits)++;
             c->nodes++;
-            float tn0, tn1;
-            int h0 = nd->child0 != 0x7fffffff && bvh_slab(nd->c0, nd->e0, invd, ood, best_t, &tn0);
-            int h1 = nd->child1 != 0x7fffffff && bvh_slab(nd->c1, nd->e1, invd, ood, best_t, &tn1);
-            if (h0 && h1) {
-                if (tn1 < tn0) {
-                    stack_ref[sp] = nd->child0; stack_tn[sp] = tn0; sp++;
-                    cur = nd->child1;
+            const float* cs[4] = {nd->c0, nd->c1, nd->c2, nd->c3};
+            const float* es[4] = {nd->e0, nd->e1, nd->e2, nd->e3};
+            const int32_t refs[4] = {nd->child0, nd->child1, nd->child2, nd->child3};
+            uint32_t key[4];
+            int hit[4];
+            for (int k = 0; k < 4; k++) {
+                float tn;
+                hit[k] = bvh_slab(cs[k], es[k], invd, ood, best_t, &tn);
+                key[k] = hit[k] ? ((f2u(tn) & ~3u) | (uint32_t)k) : 0xffffffffu;
+            }
+            if (hit[0] || hit[1] || hit[2] || hit[3]) {
+                if (any_hit) {
+                    int first = -1;
+                    for (int k = 3; k >= 0; k--) {
+                        if (!hit[k]) continue;
+                        if (first >= 0) { stack_ref[sp] = refs[first]; stack_tn[sp] = 0.0f; sp++; }
+                        first = k;
+                    }
+                    cur = refs[first];
                 } else {
-                    stack_ref[sp] = nd->child1; stack_tn[sp] = tn1; sp++;
-                    cur = nd->child0;
+#define ORA_CSWAP(a, b) do { uint32_t lo_ = key[a] < key[b] ? key[a] : key[b], hi_ = key[a] < key[b] ? key[b] : key[a]; key[a] = lo_; key[b] = hi_; } while (0)
+                    ORA_CSWAP(0, 1); ORA_CSWAP(2, 3); ORA_CSWAP(0, 2); ORA_CSWAP(1, 3); ORA_CSWAP(1, 2);
+#undef ORA_CSWAP
+                    for (int k = 3; k >= 1; k--)
+                        if (key[k] != 0xffffffffu) {
+                            uint32_t tb = key[k] & ~3u;
+                            float tnk;
+                            memcpy(&tnk, &tb, 4);
+                            stack_ref[sp] = refs[key[k] & 3u]; stack_tn[sp] = tnk; sp++;
+                        }
+                    cur = refs[key[0] & 3u];
                 }
-                continue;
-            } else if (h0) {
-                cur = nd->child0;
-                continue;
-            } else if (h1) {
-                cur = nd->child1;
-                continue;
+                descend = 1;
             }
         } else {
             uint32_t code = (uint32_t)(~cur);
@@ -484,6 +500,7 @@ static int bvh_query(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, f
                 }
             }
         }
+        if (descend) continue;
         /* pop */
         for (;;) {
             if (sp == 0) {
@@ -496,7 +513,7 @@ static int bvh_query(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, f
             }
             sp--;
             cur = stack_ref[sp];
-            if (stack_tn[sp] <= best_t) break;
+            if (any_hit || stack_tn[sp] <= best_t) break;
         }
     }
 }

@@ -55,15 +55,23 @@ typedef struct ora_triangle {
 /* BUILD-DEFINED acceleration structure, consumed as DATA (built by the product's
  * host builder, validated structurally by tests): same byte layout as
  * include/SharedHeader.h:ptb_bvh_node.                                         */
-typedef struct ora_bvh_node {
+typedef struct ora_bvh_node { /* 4-wide, 128 bytes */
     float c0[3]; /* child-0 box centre      */
     int32_t child0;
     float e0[3]; /* child-0 box half-extent */
     int32_t child1;
     float c1[3];
-    int32_t pad0;
+    int32_t child2;
     float e1[3];
+    int32_t child3;
+    float c2[3];
+    int32_t pad0;
+    float e2[3];
     int32_t pad1;
+    float c3[3];
+    int32_t pad2;
+    float e3[3];
+    int32_t pad3;
 } ora_bvh_node;
 
 typedef struct ora_bvh {

@@ -25,7 +25,7 @@ def test_struct_sizes_match_reference_layout(pt):
     assert pt.TRIANGLE_DTYPE.itemsize == 64 and pt.MATERIAL_DTYPE.itemsize == 64
     assert pt.TRIANGLE_DTYPE.fields["id"][1] == 48
     assert pt.MATERIAL_DTYPE.fields["roughness"][1] == 32 and pt.MATERIAL_DTYPE.fields["type"][1] == 36
-    assert pt.NODE_DTYPE.itemsize == 64 and pt.BVH_TRI_DTYPE.itemsize == 48 and pt.STATS_DTYPE.itemsize == 32
+    assert pt.NODE_DTYPE.itemsize == 128 and pt.BVH_TRI_DTYPE.itemsize == 48 and pt.STATS_DTYPE.itemsize == 32
     assert C.sizeof(pt.RenderParams) % 4 == 0 and C.sizeof(pt.Counters) == 64
 
 
@@ -76,12 +76,19 @@ def _validate_bvh(pt, tris, b, pad_min=0.0):
         assert not seen_nodes[ref]
         seen_nodes[ref] = True
         nd = nodes[ref]
-        l0, h0 = bounds(int(nd["child0"]))
-        l1, h1 = bounds(int(nd["child1"]))
-        for (l, h, c, e) in ((l0, h0, nd["c0"], nd["e0"]), (l1, h1, nd["c1"], nd["e1"])):  # box = [c - e, c + e]
-            c, e = c.astype(np.float64), e.astype(np.float64)
+        lo_all, hi_all, used = [], [], 0
+        for k in range(4):  # 4-wide node: box k = [c_k - e_k, c_k + e_k]
+            ch = int(nd[f"child{k}"])
+            c, e = nd[f"c{k}"].astype(np.float64), nd[f"e{k}"].astype(np.float64)
+            if ch == 0x7FFFFFFF:
+                assert (e < 0).all()  # unused slot: can never be hit
+                continue
+            used += 1
+            l, h = bounds(ch)
             assert (e > 0).all() and (c - e <= l - pad_min).all() and (c + e >= h + pad_min).all()
-        return np.minimum(l0, l1), np.maximum(h0, h1)
+            lo_all.append(l); hi_all.append(h)
+        assert used >= 2
+        return np.minimum.reduce(lo_all), np.maximum.reduce(hi_all)
 
     import sys
     sys.setrecursionlimit(10000)
@@ -92,7 +99,7 @@ def _validate_bvh(pt, tris, b, pad_min=0.0):
 def test_bvh_structure_cornell(pt, cornell):
     tris, _ = cornell
     b = pt.build_bvh_host(tris)
-    assert b["smem_nodes"] == len(b["nodes"]) <= 35 and 1 <= b["depth"] <= 12
+    assert b["smem_nodes"] == len(b["nodes"]) <= 17 and 1 <= b["depth"] <= 8
     _validate_bvh(pt, tris, b, pad_min=5e-4)  # default pad = 1e-4 * diagonal(9.6) ~ 9.6e-4
 
 
@@ -104,14 +111,15 @@ def test_bvh_structure_tessellated(pt, cornell, k, max_leaf):
     assert b["smem_nodes"] == min(64, len(b["nodes"]))
     _validate_bvh(pt, big, b, pad_min=5e-4)
     # breadth-first prefix: children of early nodes come later, prefix is closed under "parent of"
-    kids = np.concatenate([b["nodes"]["child0"], b["nodes"]["child1"]])
-    assert (kids[kids >= 0] > 0).all()
+    kids = np.concatenate([b["nodes"][f"child{k}"] for k in range(4)])
+    assert (kids[(kids >= 0) & (kids != 0x7FFFFFFF)] > 0).all()
 
 
 def test_bvh_degenerate_inputs(pt, cornell):
     tris, _ = cornell
     one = pt.build_bvh_host(tris[:1])
     assert len(one["nodes"]) == 1 and one["nodes"]["child0"][0] == one["nodes"]["child1"][0] < 0
+    assert one["nodes"]["child2"][0] == one["nodes"]["child3"][0] == 0x7FFFFFFF
     same = np.repeat(tris[:1], 9)  # identical centroids: no bin separates them -> median split fallback
     b = pt.build_bvh_host(same)
     _validate_bvh(pt, same, b)
