@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(128) k_mega(const SceneDev sc, const RenderArg
 // slot from a global counter (one warp-aggregated atomicAdd per refill), so every warp iteration is one
 // path segment for (nearly) 32 live lanes.  Per-sample arithmetic is unchanged -> identical results.
 template <bool BVH, bool SMALL, bool STATS>
-__global__ void __launch_bounds__(128) k_mega_path_regen(const SceneDev sc, const RenderArgs a,
+__global__ void __launch_bounds__(128, 8) k_mega_path_regen(const SceneDev sc, const RenderArgs a,
                                                          unsigned long long* work_counter) {
     extern __shared__ __align__(16) unsigned char smem[];
     Ctx c = stage_scene<BVH, SMALL>(sc, smem);

@@ -418,9 +418,9 @@ static inline int bvh_slab(const float c[3], const float e[3], const float invd[
 
 /* BUILD-DEFINED traversal over the 4-wide tree (the specification of node-visit counts):
  *  - `cur` >= 0: fetch the node (visits++), slab-test its four child boxes against [0, best_t].
- *      closest-hit: the hit children are ordered by the key (bits of their entry distance tn with the two
- *        low mantissa bits replaced by the slot index) ascending; descend into the first, push the others
- *        so that the nearer pops first, each with its truncated entry distance (key & ~3);
+ *      closest-hit: descend into the NEAREST hit child = smallest key (bits of its entry distance tn with the
+ *        two low mantissa bits replaced by the slot index); push the other hit children so that the lower
+ *        slot pops first, each with its entry distance tn;
  *      any-hit: descend into the hit child with the lowest slot index, push the others so that the lower
  *        slot pops first.
  *  - `cur` < 0: leaf; test its triangles in stored order.  Closest: accept when t < best_t, or t == best_t
@@ -451,11 +451,11 @@ static int bvh_query(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, f
             const float* es[4] = {nd->e0, nd->e1, nd->e2, nd->e3};
             const int32_t refs[4] = {nd->child0, nd->child1, nd->child2, nd->child3};
             uint32_t key[4];
+            float tnv[4];
             int hit[4];
             for (int k = 0; k < 4; k++) {
-                float tn;
-                hit[k] = bvh_slab(cs[k], es[k], invd, ood, best_t, &tn);
-                key[k] = hit[k] ? ((f2u(tn) & ~3u) | (uint32_t)k) : 0xffffffffu;
+                hit[k] = bvh_slab(cs[k], es[k], invd, ood, best_t, &tnv[k]);
+                key[k] = hit[k] ? ((f2u(tnv[k]) & ~3u) | (uint32_t)k) : 0xffffffffu;
             }
             if (hit[0] || hit[1] || hit[2] || hit[3]) {
                 if (any_hit) {
@@ -467,17 +467,11 @@ static int bvh_query(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, f
                     }
                     cur = refs[first];
                 } else {
-#define ORA_CSWAP(a, b) do { uint32_t lo_ = key[a] < key[b] ? key[a] : key[b], hi_ = key[a] < key[b] ? key[b] : key[a]; key[a] = lo_; key[b] = hi_; } while (0)
-                    ORA_CSWAP(0, 1); ORA_CSWAP(2, 3); ORA_CSWAP(0, 2); ORA_CSWAP(1, 3); ORA_CSWAP(1, 2);
-#undef ORA_CSWAP
-                    for (int k = 3; k >= 1; k--)
-                        if (key[k] != 0xffffffffu) {
-                            uint32_t tb = key[k] & ~3u;
-                            float tnk;
-                            memcpy(&tnk, &tb, 4);
-                            stack_ref[sp] = refs[key[k] & 3u]; stack_tn[sp] = tnk; sp++;
-                        }
-                    cur = refs[key[0] & 3u];
+                    uint32_t kmin = 0xffffffffu;
+                    for (int k = 0; k < 4; k++) if (key[k] < kmin) kmin = key[k];
+                    for (int k = 3; k >= 0; k--)
+                        if (hit[k] && key[k] != kmin) { stack_ref[sp] = refs[k]; stack_tn[sp] = tnv[k]; sp++; }
+                    cur = refs[kmin & 3u];
                 }
                 descend = 1;
             }
