@@ -389,7 +389,8 @@ def main():
     nodes_per_ray = stat_ctr["nodes"] / max(1, stat_ctr["rays_closest"] + stat_ctr["rays_any"])
     tests_per_ray = stat_ctr["tri_tests"] / max(1, stat_ctr["rays_closest"] + stat_ctr["rays_any"])
     q_bytes_per_ray = 16.0 * npix / n_rays_1  # one float4 radiance sample written per pixel-frame by the integrator
-    bytes_per_ray = nodes_per_ray * 128 + tests_per_ray * 48 + q_bytes_per_ray   # SURVEY.md 8(d), 128-byte 4-wide nodes
+    node_bytes = 128 if scene.info()["width"] == 4 else 64
+    bytes_per_ray = nodes_per_ray * node_bytes + tests_per_ray * 48 + q_bytes_per_ray
     integ_ms = prof["integrator_ms"] / max(1, prof["batches"])
     rays_per_launch = n_rays_1 / max(1, prof["batches"] / args.steps)
     achieved_gbs = bytes_per_ray * rays_per_launch / (integ_ms * 1e-3) / 1e9
@@ -403,7 +404,7 @@ def main():
             "traffic": traffic, "peak_source": peak_src, "kernel": "k_mega<AO>" if wl["mode"] == 1 else "integrator",
             "kernel_ms": integ_ms, "kernel_share_of_step": prof["integrator_ms"] / ms_steps if ms_steps else None,
             "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tri_tests_per_ray": tests_per_ray,
-            "note": "algorithmic bytes = nodes*128 + tri_tests*48 + 16 B/sample (SURVEY 8d); the 5 KB scene is shared-memory resident, so this "
+            "note": "algorithmic bytes = nodes*(128 B 4-wide | 64 B binary) + tri_tests*48 + 16 B/sample (SURVEY 8d); the 5 KB scene is shared-memory resident, so this "
                     "is the ON-CHIP stream, not DRAM traffic: the binding limit is fp32 issue (see simt)"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------------
@@ -420,13 +421,13 @@ def main():
                                    max_depth=wl.get("max_depth", 16), light_p1=light[0], light_ea=light[1], light_eb=light[2])
             _, _, oc = ob.render(op, otris, omats, bvh=bvh)
             nr = oc["rays_closest"] + oc["rays_any"]
-            flops_per_ray = (4 * oc["nodes"] * 24 + oc["tri_tests"] * 14 + oc["tri_u"] * 10 + oc["tri_v"] * 15 + oc["tri_t"] * 6 + oc["tri_accept"] * 40) / nr
+            flops_per_ray = ((node_bytes // 32) * oc["nodes"] * 24 + oc["tri_tests"] * 14 + oc["tri_u"] * 10 + oc["tri_v"] * 15 + oc["tri_t"] * 6 + oc["tri_accept"] * 40) / nr
             sm_mhz = clocks.get("sm_mhz") or sm_max_mhz
             peak_lane_ops = sm_count * 128 * sm_max_mhz * 1e6  # no FMA in the parity build: 1 lane-op per lane per clock
             ach = flops_per_ray * (rays_per_launch / (integ_ms * 1e-3))
             roof["simt"] = {"bound": "fp32_issue", "flops_per_ray": flops_per_ray, "achieved_tlaneops": ach / 1e12,
                             "peak_tlaneops": peak_lane_ops / 1e12, "frac": ach / peak_lane_ops, "sm_mhz_during_run": sm_mhz,
-                            "note": "algorithmic fp32 ops of traversal only (slab 24/box x 4 boxes per node, MT stages 14/10/15/6/40); shading, RNG and sincos are extra"}
+                            "note": "algorithmic fp32 ops of traversal only (slab 24/box x boxes per node, MT stages 14/10/15/6/40); shading, RNG and sincos are extra"}
         cpu.pop("seconds"); cpu.pop("rays"); cpu.pop("frames"); cpu.pop("wh")
 
     ab = None

@@ -52,16 +52,30 @@ typedef struct ptb_triangle {
 
 /* ---- B200-side records (BUILD-DEFINED; the reference has no BVH) ---------- */
 
-/* One internal BVH node = 8 x 128-bit words, 128-byte aligned: a 4-WIDE node
- * holding the (padded) boxes of up to FOUR children, so one coalesced 128-byte
- * fetch decides four descents (half as many dependent fetches per ray as a
- * binary tree).  Boxes are stored as CENTRE and HALF-EXTENT (box = [c - e, c + e]):
- * the slab test is then three FMAs per axis and needs no per-axis min/max
- * (t_centre = c*invd - o*invd, t_near = t_centre - e*|invd|, t_far = t_centre + e*|invd|).
- * Child reference: >= 0 internal node index; < 0 leaf, decoded as
- * first = (~ref) >> 3, count = ((~ref) & 7) + 1 into the ordered triangle
- * array; PTB_BVH_EMPTY = unused slot (its box has e = -1e30 and never hits).   */
+/* BVH nodes hold the (padded) boxes of their CHILDREN, so one coalesced fetch decides every descent from
+ * that node.  Boxes are stored as CENTRE and HALF-EXTENT (box = [c - e, c + e]): the slab test is then three
+ * FMAs per axis and needs no per-axis min/max (t_centre = c*invd - o*invd, t_near = t_centre - e*|invd|,
+ * t_far = t_centre + e*|invd|).  Child reference: >= 0 internal node index; < 0 leaf, decoded as
+ * first = (~ref) >> 3, count = ((~ref) & 7) + 1 into the ordered triangle array; PTB_BVH_EMPTY = unused slot
+ * (its box has e = -1e30 and never hits).
+ *
+ * Two node widths, chosen per scene:
+ *   ptb_bvh_node   binary, 4 x 128-bit words = 64 B  -- scenes traversed from L2/HBM (fewest bytes and registers
+ *                                                        per visit; measured best on the 2M-triangle scene)
+ *   ptb_bvh_node4  4-wide, 8 x 128-bit words = 128 B -- scenes that live entirely in shared memory (half as many
+ *                                                        loop iterations per ray; measured +8 % on Cornell AO)   */
 typedef struct ptb_bvh_node {
+    float c0[3];
+    int32_t child0; /* word 0: child-0 centre,      child-0 ref */
+    float e0[3];
+    int32_t child1; /* word 1: child-0 half-extent, child-1 ref */
+    float c1[3];
+    int32_t pad0; /* word 2: child-1 centre */
+    float e1[3];
+    int32_t pad1; /* word 3: child-1 half-extent */
+} ptb_bvh_node;
+
+typedef struct ptb_bvh_node4 {
     float c0[3];
     int32_t child0; /* word 0: child-0 centre,      child-0 ref */
     float e0[3];
@@ -78,9 +92,9 @@ typedef struct ptb_bvh_node {
     int32_t pad2;
     float e3[3];
     int32_t pad3;
-} ptb_bvh_node;
-#define PTB_BVH_WIDTH 4
+} ptb_bvh_node4;
 
+#define PTB_BVH_WIDTH 4 /* slots of a ptb_bvh_node4 */
 #define PTB_BVH_EMPTY 0x7fffffff
 #define PTB_BVH_LEAF_REF(first, count) (~(int32_t)(((uint32_t)(first) << 3) | (uint32_t)((count)-1)))
 #define PTB_BVH_LEAF_FIRST(ref) ((int32_t)((uint32_t)(~(ref)) >> 3))
@@ -145,7 +159,7 @@ typedef struct ptb_render_params {
 typedef struct ptb_counters {
     uint64_t rays_closest; /* closest-hit queries */
     uint64_t rays_any;     /* any-hit (shadow / AO) queries */
-    uint64_t nodes;        /* internal BVH node records fetched (4 slab tests each) */
+    uint64_t nodes;        /* internal BVH node records fetched (2 or 4 slab tests each) */
     uint64_t tri_tests;    /* Moller-Trumbore tests started (det stage) */
     uint64_t samples;      /* pixel-frames */
     uint64_t reserved[3];
@@ -156,7 +170,8 @@ typedef struct ptb_counters {
 #if __cplusplus >= 201103L
 static_assert(sizeof(ptb_material) == 64, "Material must be 64 bytes (RaytraceTest.cpp:50-59)");
 static_assert(sizeof(ptb_triangle) == 64, "Triangle must be 64 bytes (RaytraceTest.cpp:61-76)");
-static_assert(sizeof(ptb_bvh_node) == 128, "BVH node must be 128 bytes");
+static_assert(sizeof(ptb_bvh_node) == 64, "binary BVH node must be 64 bytes");
+static_assert(sizeof(ptb_bvh_node4) == 128, "4-wide BVH node must be 128 bytes");
 static_assert(sizeof(ptb_bvh_tri) == 48, "BVH triangle must be 48 bytes");
 #endif
 #endif

@@ -127,8 +127,9 @@ typedef struct ptb_bvh_params {
 } ptb_bvh_params;
 void ptb_bvh_params_default(ptb_bvh_params* p);
 
-/* host-only build (no device needed): returns malloc'd arrays, release with ptb_free */
-int ptb_bvh_build_host(const ptb_triangle* tris, int n_tris, const ptb_bvh_params* bvh_params, ptb_bvh_node** nodes,
+/* host-only build (no device needed): returns malloc'd arrays, release with ptb_free.  width = 2: ptb_bvh_node
+ * records; width = 4: ptb_bvh_node4 records (the same tree collapsed; built for scenes of <= 2048 triangles) */
+int ptb_bvh_build_host(const ptb_triangle* tris, int n_tris, const ptb_bvh_params* bvh_params, int width, void** nodes,
                        int* n_nodes, int32_t** tri_order, ptb_bvh_tri** ordered_tris, int* depth, int* smem_nodes);
 
 int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats, int n_mats,
@@ -139,8 +140,10 @@ int ptb_scene_create_gpu(ptb_device* dev, const ptb_triangle* tris, int n_tris, 
                          const ptb_bvh_params* bvh_params /* NULL = default */, ptb_scene** out);
 int ptb_scene_destroy(ptb_scene* scene);
 int ptb_scene_info(ptb_scene* scene, int* n_nodes, int* n_tris, int* depth, int* smem_nodes);
-/* host copies of the built tree, for structural validation and the oracle */
-int ptb_scene_copy_bvh(ptb_scene* scene, ptb_bvh_node* nodes, int32_t* tri_order);
+/* node width of the resident tree: 4 (ptb_bvh_node4, scenes that fit a 32 KB shared-memory budget) or 2 */
+int ptb_scene_bvh_width(ptb_scene* scene);
+/* host copies of the built tree (n_nodes records of the scene's width), for structural validation and tests */
+int ptb_scene_copy_bvh(ptb_scene* scene, void* nodes, int32_t* tri_order);
 
 /* ---- the hot path -------------------------------------------------------------------
  * per-pixel statistics of the LAST frame of a call (collect_stats = 1)          */

@@ -24,7 +24,13 @@ TRIANGLE_DTYPE = np.dtype(
 MATERIAL_DTYPE = np.dtype(
     [("albedo", "<f4", 4), ("emissive", "<f4", 4), ("roughness", "<f4"), ("type", "<i4"), ("padding", "u1", 24)]
 )
-NODE_DTYPE = np.dtype(
+NODE_DTYPE = np.dtype(  # binary node, 64 bytes (ptb_bvh_node)
+    [
+        ("c0", "<f4", 3), ("child0", "<i4"), ("e0", "<f4", 3), ("child1", "<i4"),
+        ("c1", "<f4", 3), ("pad0", "<i4"), ("e1", "<f4", 3), ("pad1", "<i4"),
+    ]
+)
+NODE4_DTYPE = np.dtype(  # 4-wide node, 128 bytes (ptb_bvh_node4)
     [
         ("c0", "<f4", 3), ("child0", "<i4"), ("e0", "<f4", 3), ("child1", "<i4"),
         ("c1", "<f4", 3), ("child2", "<i4"), ("e1", "<f4", 3), ("child3", "<i4"),
@@ -86,7 +92,7 @@ EXPORTS = [
     "ptb_buffer_map", "ptb_buffer_unmap", "ptb_buffer_clear", "ptb_buffer_device_ptr", "ptb_buffer_size",
     "ptb_kernel_get", "ptb_kernel_set_int", "ptb_launch1d", "ptb_launch_serialize", "ptb_launch_deserialize", "ptb_load_model", "ptb_tessellate",
     "ptb_light_from_quad", "ptb_free", "ptb_to_rgb8", "ptb_write_ppm", "ptb_bvh_params_default",
-    "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_create_gpu", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_copy_bvh",
+    "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_create_gpu", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_bvh_width", "ptb_scene_copy_bvh",
     "ptb_render_params_default", "ptb_render_local_pixels", "ptb_render", "ptb_render_host",
     "ptb_render_host_async", "ptb_job_wait", "ptb_host_alloc", "ptb_host_free", "ptb_trace",
     "ptb_device_profile", "ptb_device_profile_read", "ptb_device_set_tuning", "ptb_test_sincos", "ptb_test_pow", "ptb_test_rng", "ptb_test_camera",
@@ -126,7 +132,8 @@ def lib():
         L.ptb_device_sm_count.argtypes = [C.c_void_p, C.c_void_p]
         L.ptb_device_stream.argtypes = [C.c_void_p]
         L.ptb_device_memory.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        L.ptb_bvh_build_host.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        L.ptb_bvh_build_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6
+        L.ptb_scene_bvh_width.argtypes = [C.c_void_p]
         L.ptb_scene_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptb_scene_create_gpu.argtypes = L.ptb_scene_create.argtypes
         L.ptb_scene_info.argtypes = [C.c_void_p] + [C.c_void_p] * 4
@@ -225,18 +232,26 @@ BVH_TRI_DTYPE = np.dtype(
 )
 
 
-def build_bvh_host(tris, params=None):
-    """Host-only BVH build (no GPU): dict(nodes, tri_order, ordered_tris, depth, smem_nodes)."""
+def build_bvh_host(tris, params=None, width=None):
+    """Host-only BVH build (no GPU): dict(nodes, tri_order, ordered_tris, depth, smem_nodes, width).
+
+    width 4 -> NODE4_DTYPE records (what a shared-memory-resident scene uses), 2 -> NODE_DTYPE;
+    None picks like ptb_scene_create does for the Cornell-sized scenes of the tests (4 when <= 256 triangles).
+    """
     L = lib()
     tris = np.ascontiguousarray(tris)
+    if width is None:
+        width = 4 if len(tris) <= 256 else 2
     nodes, order, otris = C.c_void_p(), C.c_void_p(), C.c_void_p()
     nn, depth, sn = C.c_int(), C.c_int(), C.c_int()
-    _check(L.ptb_bvh_build_host(_p(tris), len(tris), C.byref(params) if params is not None else None,
+    _check(L.ptb_bvh_build_host(_p(tris), len(tris), C.byref(params) if params is not None else None, width,
                                 C.byref(nodes), C.byref(nn), C.byref(order), C.byref(otris), C.byref(depth),
                                 C.byref(sn)))
+    dt = NODE4_DTYPE if width == 4 else NODE_DTYPE
     try:
         res = {
-            "nodes": np.frombuffer(C.string_at(nodes, nn.value * 128), NODE_DTYPE).copy(),
+            "width": width,
+            "nodes": np.frombuffer(C.string_at(nodes, nn.value * dt.itemsize), dt).copy(),
             "tri_order": np.frombuffer(C.string_at(order, len(tris) * 4), np.int32).copy(),
             "ordered_tris": np.frombuffer(C.string_at(otris, len(tris) * 48), BVH_TRI_DTYPE).copy(),
             "depth": depth.value, "smem_nodes": sn.value,
@@ -486,11 +501,12 @@ class Scene:
     def info(self):
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _check(lib().ptb_scene_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
-        return {"n_nodes": a.value, "n_tris": b.value, "depth": c.value, "smem_nodes": d.value}
+        return {"n_nodes": a.value, "n_tris": b.value, "depth": c.value, "smem_nodes": d.value,
+                "width": lib().ptb_scene_bvh_width(self._h)}
 
     def bvh(self):
         inf = self.info()
-        nodes = np.zeros(inf["n_nodes"], NODE_DTYPE)
+        nodes = np.zeros(inf["n_nodes"], NODE4_DTYPE if inf["width"] == 4 else NODE_DTYPE)
         order = np.zeros(inf["n_tris"], np.int32)
         _check(lib().ptb_scene_copy_bvh(self._h, _p(nodes), _p(order)))
         return nodes, order

@@ -2,8 +2,9 @@
 // has no acceleration structure; every ray loops over NUM_TRIANGLES,
 // test/ClKernels/GenerateColors.cl:137-154).
 //
-// Output format (include/SharedHeader.h): 128-byte 4-wide nodes holding their
-// children's padded boxes (centre/half-extent), 48-byte precomputed-edge triangles in leaf order.
+// Output format (include/SharedHeader.h): binary 64-byte nodes (and, for small scenes, the same tree
+// collapsed to 128-byte 4-wide nodes) holding their children's padded boxes as centre/half-extent,
+// 48-byte precomputed-edge triangles in leaf order.
 // The tree must be EQUIVALENT to the brute-force loop: traversal may only skip
 // triangles the Moller-Trumbore test would reject, so every stored box is the
 // exact fp32 bound of its triangles grown by an absolute pad (pad_rel x scene
@@ -212,68 +213,20 @@ int build_bvh(const ptb_triangle* tris, int n_tris, const ptb_bvh_params& params
     const float diag = std::sqrt(dx * dx + dy * dy + dz * dz);
     const float pad = std::max(params.pad_rel, 0.0f) * diag;
 
-    // collapse the binary tree into 4-wide nodes: start from a node's two children and keep replacing the
-    // internal child with the largest box (ties: lowest slot) by its own two children, in place, until four
-    // slots are used or only leaves remain.
-    struct Wide {
-        int32_t child[PTB_BVH_WIDTH];
-        Box box[PTB_BVH_WIDTH];
-        int n = 0;
-    };
-    std::vector<Wide> wide;
-    wide.reserve(B.nodes.size() / 2 + 1);
-    {
-        struct Item { int32_t bin; int32_t wide_parent; int slot; };
-        std::vector<Item> todo{{0, -1, 0}};
-        while (!todo.empty()) {
-            const Item it = todo.back();
-            todo.pop_back();
-            std::vector<std::pair<int32_t, Box>> slots;
-            slots.push_back({B.nodes[it.bin].child[0], B.nodes[it.bin].box[0]});
-            slots.push_back({B.nodes[it.bin].child[1], B.nodes[it.bin].box[1]});
-            while (int(slots.size()) < PTB_BVH_WIDTH) {
-                int pick = -1;
-                double best = -1.0;
-                for (int k = 0; k < int(slots.size()); ++k)
-                    if (slots[k].first >= 0 && slots[k].second.half_area() > best) { best = slots[k].second.half_area(); pick = k; }
-                if (pick < 0) break;
-                const TmpNode& t = B.nodes[slots[pick].first];
-                const std::pair<int32_t, Box> l{t.child[0], t.box[0]}, r{t.child[1], t.box[1]};
-                slots[pick] = l;
-                slots.insert(slots.begin() + pick + 1, r);
-            }
-            const int32_t me = int32_t(wide.size());
-            wide.emplace_back();
-            if (it.wide_parent >= 0) wide[it.wide_parent].child[it.slot] = me;
-            wide[me].n = int(slots.size());
-            for (int k = 0; k < PTB_BVH_WIDTH; ++k) {
-                if (k < int(slots.size())) {
-                    wide[me].child[k] = slots[k].first;  // binary index for now (>= 0) or a leaf reference
-                    wide[me].box[k] = slots[k].second;
-                } else {
-                    wide[me].child[k] = PTB_BVH_EMPTY;
-                }
-            }
-            for (int k = int(slots.size()) - 1; k >= 0; --k)  // reverse push -> children are numbered in slot order
-                if (slots[k].first >= 0) todo.push_back({slots[k].first, me, k});
-        }
-    }
-
     // renumber: breadth-first prefix, then depth-first subtrees
-    const int n_nodes = int(wide.size());
+    const int n_nodes = int(B.nodes.size());
     const int want_bfs = std::min(std::max(params.smem_nodes, 1), n_nodes);
     std::vector<int32_t> new_of(size_t(n_nodes), -1);
     std::vector<int32_t> old_of;
     old_of.reserve(size_t(n_nodes));
-    auto internal = [](int32_t ref) { return ref >= 0 && ref != PTB_BVH_EMPTY; };
     std::deque<int32_t> queue{0};
     while (!queue.empty() && int(old_of.size()) < want_bfs) {
         const int32_t o = queue.front();
         queue.pop_front();
         new_of[o] = int32_t(old_of.size());
         old_of.push_back(o);
-        for (int c = 0; c < PTB_BVH_WIDTH; ++c)
-            if (internal(wide[o].child[c])) queue.push_back(wide[o].child[c]);
+        for (int c = 0; c < 2; ++c)
+            if (B.nodes[o].child[c] >= 0) queue.push_back(B.nodes[o].child[c]);
     }
     const int bfs_count = int(old_of.size());
     std::vector<int32_t> stack;
@@ -284,29 +237,25 @@ int build_bvh(const ptb_triangle* tris, int n_tris, const ptb_bvh_params& params
             stack.pop_back();
             new_of[o] = int32_t(old_of.size());
             old_of.push_back(o);
-            for (int c = PTB_BVH_WIDTH - 1; c >= 0; --c)
-                if (internal(wide[o].child[c])) stack.push_back(wide[o].child[c]);
+            if (B.nodes[o].child[1] >= 0) stack.push_back(B.nodes[o].child[1]);
+            if (B.nodes[o].child[0] >= 0) stack.push_back(B.nodes[o].child[0]);
         }
     }
     if (int(old_of.size()) != n_nodes) return fail(PTB_E_INVALID, "build_bvh: renumbering lost nodes");
 
     out->nodes.assign(size_t(n_nodes), ptb_bvh_node{});
     for (int ni = 0; ni < n_nodes; ++ni) {
-        const Wide& t = wide[old_of[ni]];
+        const TmpNode& t = B.nodes[old_of[ni]];
         ptb_bvh_node& d = out->nodes[ni];
-        float* cs[PTB_BVH_WIDTH] = {d.c0, d.c1, d.c2, d.c3};
-        float* es[PTB_BVH_WIDTH] = {d.e0, d.e1, d.e2, d.e3};
-        int32_t* refs[PTB_BVH_WIDTH] = {&d.child0, &d.child1, &d.child2, &d.child3};
-        for (int k = 0; k < PTB_BVH_WIDTH; ++k) {
-            *refs[k] = internal(t.child[k]) ? new_of[t.child[k]] : t.child[k];
-            for (int a = 0; a < 3; ++a) {
-                if (t.child[k] == PTB_BVH_EMPTY) { cs[k][a] = 0.0f; es[k][a] = -1e30f; }
-                else centre_extent(t.box[k].lo[a] - pad, t.box[k].hi[a] + pad, &cs[k][a], &es[k][a]);
-            }
+        d.child0 = t.child[0] >= 0 ? new_of[t.child[0]] : t.child[0];
+        d.child1 = t.child[1] >= 0 ? new_of[t.child[1]] : t.child[1];
+        for (int a = 0; a < 3; ++a) {
+            centre_extent(t.box[0].lo[a] - pad, t.box[0].hi[a] + pad, &d.c0[a], &d.e0[a]);
+            centre_extent(t.box[1].lo[a] - pad, t.box[1].hi[a] + pad, &d.c1[a], &d.e1[a]);
         }
-        d.pad0 = d.pad1 = d.pad2 = d.pad3 = 0;
+        d.pad0 = d.pad1 = 0;
     }
-    // depth = longest chain of internal nodes (bounds the traversal stack: up to 3 deferred children per level)
+    // depth = longest chain of internal nodes (bounds the traversal stack)
     int depth = 1;
     {
         std::vector<std::pair<int32_t, int>> st{{0, 1}};
@@ -314,13 +263,124 @@ int build_bvh(const ptb_triangle* tris, int n_tris, const ptb_bvh_params& params
             auto [ni, dep] = st.back();
             st.pop_back();
             depth = std::max(depth, dep);
-            const int32_t refs[PTB_BVH_WIDTH] = {out->nodes[ni].child0, out->nodes[ni].child1, out->nodes[ni].child2, out->nodes[ni].child3};
-            for (int k = 0; k < PTB_BVH_WIDTH; ++k)
-                if (internal(refs[k])) st.push_back({refs[k], dep + 1});
+            if (out->nodes[ni].child0 >= 0) st.push_back({out->nodes[ni].child0, dep + 1});
+            if (out->nodes[ni].child1 >= 0) st.push_back({out->nodes[ni].child1, dep + 1});
         }
     }
     out->depth = depth;
     out->smem_nodes = bfs_count;
+
+    if (n_tris <= 2048) {  // small scenes also get the 4-wide form (shared-memory-resident traversal)
+        // collapse the binary tree into 4-wide nodes: start from a node's two children and keep replacing the
+        // internal child with the largest box (ties: lowest slot) by its own two children, in place, until four
+        // slots are used or only leaves remain.
+        struct Wide {
+            int32_t child[PTB_BVH_WIDTH];
+            Box box[PTB_BVH_WIDTH];
+            int n = 0;
+        };
+        std::vector<Wide> wide;
+        wide.reserve(B.nodes.size() / 2 + 1);
+        {
+            struct Item { int32_t bin; int32_t wide_parent; int slot; };
+            std::vector<Item> todo{{0, -1, 0}};
+            while (!todo.empty()) {
+                const Item it = todo.back();
+                todo.pop_back();
+                std::vector<std::pair<int32_t, Box>> slots;
+                slots.push_back({B.nodes[it.bin].child[0], B.nodes[it.bin].box[0]});
+                slots.push_back({B.nodes[it.bin].child[1], B.nodes[it.bin].box[1]});
+                while (int(slots.size()) < PTB_BVH_WIDTH) {
+                    int pick = -1;
+                    double best = -1.0;
+                    for (int k = 0; k < int(slots.size()); ++k)
+                        if (slots[k].first >= 0 && slots[k].second.half_area() > best) { best = slots[k].second.half_area(); pick = k; }
+                    if (pick < 0) break;
+                    const TmpNode& t = B.nodes[slots[pick].first];
+                    const std::pair<int32_t, Box> l{t.child[0], t.box[0]}, r{t.child[1], t.box[1]};
+                    slots[pick] = l;
+                    slots.insert(slots.begin() + pick + 1, r);
+                }
+                const int32_t me = int32_t(wide.size());
+                wide.emplace_back();
+                if (it.wide_parent >= 0) wide[it.wide_parent].child[it.slot] = me;
+                wide[me].n = int(slots.size());
+                for (int k = 0; k < PTB_BVH_WIDTH; ++k) {
+                    if (k < int(slots.size())) {
+                        wide[me].child[k] = slots[k].first;  // binary index for now (>= 0) or a leaf reference
+                        wide[me].box[k] = slots[k].second;
+                    } else {
+                        wide[me].child[k] = PTB_BVH_EMPTY;
+                    }
+                }
+                for (int k = int(slots.size()) - 1; k >= 0; --k)  // reverse push -> children are numbered in slot order
+                    if (slots[k].first >= 0) todo.push_back({slots[k].first, me, k});
+            }
+        }
+
+        // renumber: breadth-first prefix, then depth-first subtrees
+        const int n_nodes = int(wide.size());
+        const int want_bfs = std::min(std::max(params.smem_nodes, 1), n_nodes);
+        std::vector<int32_t> new_of(size_t(n_nodes), -1);
+        std::vector<int32_t> old_of;
+        old_of.reserve(size_t(n_nodes));
+        auto internal = [](int32_t ref) { return ref >= 0 && ref != PTB_BVH_EMPTY; };
+        std::deque<int32_t> queue{0};
+        while (!queue.empty() && int(old_of.size()) < want_bfs) {
+            const int32_t o = queue.front();
+            queue.pop_front();
+            new_of[o] = int32_t(old_of.size());
+            old_of.push_back(o);
+            for (int c = 0; c < PTB_BVH_WIDTH; ++c)
+                if (internal(wide[o].child[c])) queue.push_back(wide[o].child[c]);
+        }
+        const int bfs_count = int(old_of.size());
+        std::vector<int32_t> stack;
+        for (int32_t root : queue) {
+            stack.push_back(root);
+            while (!stack.empty()) {
+                const int32_t o = stack.back();
+                stack.pop_back();
+                new_of[o] = int32_t(old_of.size());
+                old_of.push_back(o);
+                for (int c = PTB_BVH_WIDTH - 1; c >= 0; --c)
+                    if (internal(wide[o].child[c])) stack.push_back(wide[o].child[c]);
+            }
+        }
+        if (int(old_of.size()) != n_nodes) return fail(PTB_E_INVALID, "build_bvh: renumbering lost nodes");
+
+        out->nodes4.assign(size_t(n_nodes), ptb_bvh_node4{});
+        for (int ni = 0; ni < n_nodes; ++ni) {
+            const Wide& t = wide[old_of[ni]];
+            ptb_bvh_node4& d = out->nodes4[ni];
+            float* cs[PTB_BVH_WIDTH] = {d.c0, d.c1, d.c2, d.c3};
+            float* es[PTB_BVH_WIDTH] = {d.e0, d.e1, d.e2, d.e3};
+            int32_t* refs[PTB_BVH_WIDTH] = {&d.child0, &d.child1, &d.child2, &d.child3};
+            for (int k = 0; k < PTB_BVH_WIDTH; ++k) {
+                *refs[k] = internal(t.child[k]) ? new_of[t.child[k]] : t.child[k];
+                for (int a = 0; a < 3; ++a) {
+                    if (t.child[k] == PTB_BVH_EMPTY) { cs[k][a] = 0.0f; es[k][a] = -1e30f; }
+                    else centre_extent(t.box[k].lo[a] - pad, t.box[k].hi[a] + pad, &cs[k][a], &es[k][a]);
+                }
+            }
+            d.pad0 = d.pad1 = d.pad2 = d.pad3 = 0;
+        }
+        // depth = longest chain of internal nodes (bounds the traversal stack: up to 3 deferred children per level)
+        int depth = 1;
+        {
+            std::vector<std::pair<int32_t, int>> st{{0, 1}};
+            while (!st.empty()) {
+                auto [ni, dep] = st.back();
+                st.pop_back();
+                depth = std::max(depth, dep);
+                const int32_t refs[PTB_BVH_WIDTH] = {out->nodes4[ni].child0, out->nodes4[ni].child1, out->nodes4[ni].child2, out->nodes4[ni].child3};
+                for (int k = 0; k < PTB_BVH_WIDTH; ++k)
+                    if (internal(refs[k])) st.push_back({refs[k], dep + 1});
+            }
+        }
+        out->depth4 = depth;
+        out->smem_nodes4 = bfs_count;
+    }
     out->tri_order = B.order;
     out->tris.resize(B.order.size());
     for (size_t k = 0; k < B.order.size(); ++k) edge_tri(tris[B.order[k]], B.order[k], &out->tris[k]);

@@ -107,6 +107,7 @@ struct ptb_scene {
     float4* d_tris_orig = nullptr;
     float4* d_mats = nullptr;
     bool small = false;
+    int width = 2;                        // 4: ptb_bvh_node4 records (small scenes), 2: ptb_bvh_node
     int n_nodes = 0, depth = 0, bfs_nodes = 0;
     int* d_order = nullptr;               // GPU-built scenes: BVH position -> caller index (device)
     bool host_copy_valid = true;          // false until a GPU-built tree has been downloaded
@@ -371,16 +372,19 @@ extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n
         std::memcpy(&tbits, &mats[i].type, 4);
         m[2 * i + 1] = make_float4(mats[i].emissive.x, mats[i].emissive.y, mats[i].emissive.z, tbits);
     }
-    s->n_nodes = int(s->bvh.nodes.size()); s->depth = s->bvh.depth; s->bfs_nodes = s->bvh.smem_nodes;
-    const size_t staged = s->bvh.nodes.size() * sizeof(ptb_bvh_node) + size_t(n_tris) * 48 + size_t(n_mats) * 32;
-    s->small = staged <= 32 * 1024 && int(s->bvh.nodes.size()) == s->bvh.smem_nodes;
+    // scene class: everything (4-wide nodes, triangles, materials) fits a 32 KB shared-memory budget -> SMALL
+    const size_t staged4 = s->bvh.nodes4.size() * sizeof(ptb_bvh_node4) + size_t(n_tris) * 48 + size_t(n_mats) * 32;
+    s->small = !s->bvh.nodes4.empty() && staged4 <= 32 * 1024 && int(s->bvh.nodes4.size()) == s->bvh.smem_nodes4;
+    if (s->small) { s->width = 4; s->n_nodes = int(s->bvh.nodes4.size()); s->depth = s->bvh.depth4; s->bfs_nodes = s->bvh.smem_nodes4; }
+    else { s->width = 2; s->n_nodes = int(s->bvh.nodes.size()); s->depth = s->bvh.depth; s->bfs_nodes = s->bvh.smem_nodes; }
     if (set_device(dev)) { delete s; return PTB_E_CUDA; }
     auto up = [&](float4** d, const void* h, size_t bytes) -> int {
         CU_TRY(cudaMalloc((void**)d, bytes));
         CU_TRY(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, dev->stream));
         return PTB_OK;
     };
-    if ((rc = up(&s->d_nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptb_bvh_node))) ||
+    if ((rc = s->small ? up(&s->d_nodes, s->bvh.nodes4.data(), s->bvh.nodes4.size() * sizeof(ptb_bvh_node4))
+                       : up(&s->d_nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptb_bvh_node))) ||
         (rc = up(&s->d_tris, s->bvh.tris.data(), s->bvh.tris.size() * 48)) ||
         (rc = up(&s->d_tris_orig, orig.data(), orig.size() * 48)) || (rc = up(&s->d_mats, m.data(), m.size() * 16))) {
         ptb_scene_destroy(s);
@@ -431,7 +435,7 @@ extern "C" int ptb_scene_create_gpu(ptb_device* dev, const ptb_triangle* tris, i
     float4* d_nodes = nullptr; float4* d_otris = nullptr; int* d_order = nullptr; int depth = 0;
     if ((rc = ptd::build_lbvh_device(dev->stream, d_raw, n_tris, bp.max_leaf, bp.pad_rel, &d_nodes, &d_otris, &d_order, &depth))) return fail_out(rc);
     s->d_nodes = d_nodes; s->d_tris = d_otris; s->d_order = d_order;
-    s->n_nodes = n_tris - 1; s->depth = depth; s->bfs_nodes = 1; s->small = false;
+    s->n_nodes = n_tris - 1; s->depth = depth; s->bfs_nodes = 1; s->small = false; s->width = 2;
     auto up = [&](float4** d, const void* h, size_t bytes) -> int {
         CU_TRY(cudaMalloc((void**)d, bytes));
         CU_TRY(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, dev->stream));
@@ -444,27 +448,30 @@ extern "C" int ptb_scene_create_gpu(ptb_device* dev, const ptb_triangle* tris, i
     return PTB_OK;
 }
 
-extern "C" int ptb_bvh_build_host(const ptb_triangle* tris, int n_tris, const ptb_bvh_params* bvh_params,
-                                  ptb_bvh_node** nodes, int* n_nodes, int32_t** tri_order, ptb_bvh_tri** ordered_tris,
+extern "C" int ptb_bvh_build_host(const ptb_triangle* tris, int n_tris, const ptb_bvh_params* bvh_params, int width,
+                                  void** nodes, int* n_nodes, int32_t** tri_order, ptb_bvh_tri** ordered_tris,
                                   int* depth, int* smem_nodes) {
     if (!tris || !nodes || !n_nodes || !tri_order) return fail(PTB_E_INVALID, "ptb_bvh_build_host: null argument");
+    if (width != 2 && width != 4) return fail(PTB_E_INVALID, "ptb_bvh_build_host: width must be 2 or 4");
     ptb_bvh_params bp;
     if (bvh_params) bp = *bvh_params; else ptb_bvh_params_default(&bp);
     BuiltBvh b;
     if (int rc = build_bvh(tris, n_tris, bp, &b)) return rc;
-    *nodes = static_cast<ptb_bvh_node*>(std::malloc(b.nodes.size() * sizeof(ptb_bvh_node)));
+    if (width == 4 && b.nodes4.empty()) return fail(PTB_E_INVALID, "ptb_bvh_build_host: 4-wide trees are built for <= 2048 triangles");
+    const size_t node_bytes = width == 4 ? b.nodes4.size() * sizeof(ptb_bvh_node4) : b.nodes.size() * sizeof(ptb_bvh_node);
+    *nodes = std::malloc(node_bytes);
     *tri_order = static_cast<int32_t*>(std::malloc(b.tri_order.size() * sizeof(int32_t)));
     if (!*nodes || !*tri_order) return fail(PTB_E_NOMEM, "ptb_bvh_build_host: out of memory");
-    std::memcpy(*nodes, b.nodes.data(), b.nodes.size() * sizeof(ptb_bvh_node));
+    std::memcpy(*nodes, width == 4 ? (const void*)b.nodes4.data() : (const void*)b.nodes.data(), node_bytes);
     std::memcpy(*tri_order, b.tri_order.data(), b.tri_order.size() * sizeof(int32_t));
     if (ordered_tris) {
         *ordered_tris = static_cast<ptb_bvh_tri*>(std::malloc(b.tris.size() * sizeof(ptb_bvh_tri)));
         if (!*ordered_tris) return fail(PTB_E_NOMEM, "ptb_bvh_build_host: out of memory");
         std::memcpy(*ordered_tris, b.tris.data(), b.tris.size() * sizeof(ptb_bvh_tri));
     }
-    *n_nodes = int(b.nodes.size());
-    if (depth) *depth = b.depth;
-    if (smem_nodes) *smem_nodes = b.smem_nodes;
+    *n_nodes = int(width == 4 ? b.nodes4.size() : b.nodes.size());
+    if (depth) *depth = width == 4 ? b.depth4 : b.depth;
+    if (smem_nodes) *smem_nodes = width == 4 ? b.smem_nodes4 : b.smem_nodes;
     return PTB_OK;
 }
 
@@ -477,7 +484,9 @@ extern "C" int ptb_scene_info(ptb_scene* s, int* n_nodes, int* n_tris, int* dept
     return PTB_OK;
 }
 
-extern "C" int ptb_scene_copy_bvh(ptb_scene* s, ptb_bvh_node* nodes, int32_t* tri_order) {
+extern "C" int ptb_scene_bvh_width(ptb_scene* s) { return s ? s->width : 0; }
+
+extern "C" int ptb_scene_copy_bvh(ptb_scene* s, void* nodes, int32_t* tri_order) {
     if (!s) return fail(PTB_E_INVALID, "ptb_scene_copy_bvh: null scene");
     if (!s->host_copy_valid) {  // GPU-built tree: download on first request
         if (set_device(s->dev)) return PTB_E_CUDA;
@@ -488,7 +497,10 @@ extern "C" int ptb_scene_copy_bvh(ptb_scene* s, ptb_bvh_node* nodes, int32_t* tr
         CU_TRY(cudaStreamSynchronize(s->dev->stream));
         s->host_copy_valid = true;
     }
-    if (nodes) std::memcpy(nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptb_bvh_node));
+    if (nodes) {
+        if (s->width == 4) std::memcpy(nodes, s->bvh.nodes4.data(), s->bvh.nodes4.size() * sizeof(ptb_bvh_node4));
+        else std::memcpy(nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptb_bvh_node));
+    }
     if (tri_order) std::memcpy(tri_order, s->bvh.tri_order.data(), s->bvh.tri_order.size() * sizeof(int32_t));
     return PTB_OK;
 }
@@ -497,16 +509,15 @@ static ptd::SceneDev scene_dev(const ptb_scene* s) {
     ptd::SceneDev d;
     d.nodes = s->d_nodes; d.tris = s->d_tris; d.tris_orig = s->d_tris_orig; d.mats = s->d_mats;
     d.n_nodes = s->n_nodes; d.n_tris = s->n_tris; d.n_mats = s->n_mats;
-    // Large scenes stage only the top of the tree: a 32-node (4 KB) prefix keeps occupancy high
-    // (measured on the 2M-triangle scene with binary 64-byte nodes: 1024 nodes 0.83, 256 nodes 1.81,
-    // 64 nodes 2.28 Grays/s).
-    const int cap = s->dev->tune[4] > 0 ? s->dev->tune[4] : 32;
+    // Large scenes stage only the top of the tree: a 64-node (4 KB) prefix keeps >= 6 CTAs per SM
+    // resident (measured on the 2M-triangle scene: 1024 nodes 0.83, 256 nodes 1.81, 64 nodes 2.28 Grays/s).
+    const int cap = s->dev->tune[4] > 0 ? s->dev->tune[4] : 64;
     d.smem_nodes = s->small ? s->bfs_nodes : (s->bfs_nodes < cap ? s->bfs_nodes : cap);
     d.small = s->small ? 1 : 0;
-    d.stack_depth = 3 * s->depth + 1;  // a 4-wide visit defers up to three children
+    d.stack_depth = s->width == 4 ? 3 * s->depth + 1 : s->depth + 1;  // a 4-wide visit defers up to three children
     // scenes traversed from L2/HBM keep the stack in local memory: shared memory then holds only the node
     // prefix and occupancy is bounded by registers (C5: +2.4 %); tune[2]=2 forces the shared-memory stack
-    d.lstack = (!s->small && s->dev->tune[2] != 2 && 3 * s->depth + 1 <= PTD_LSTACK_ENTRIES) ? 1 : 0;
+    d.lstack = (!s->small && s->dev->tune[2] != 2 && s->depth + 1 <= PTD_LSTACK_ENTRIES) ? 1 : 0;
     return d;
 }
 
@@ -661,14 +672,11 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
     a.counters = dev->counters;
     for (int k = 0; k < 8; ++k) a.tune[k] = dev->tune[k];
 
-    // AUTO = the faster integrator as measured on B200: the wavefront wins where paths
-    // of very different length share a warp (PATH on a shared-memory-resident scene, >= 1 M samples in
-    // flight); the megakernel wins for the fixed-shape modes and for scenes traversed from L2/HBM.
+    // AUTO = the faster integrator as measured on B200.  With 4-wide nodes for
+    // shared-memory-resident scenes and path regeneration, the megakernel wins every BASELINE configuration
+    // (C4: 10.7 vs 9.6 Grays/s, C2: 30.7 vs 25.9, C5: 2.9 vs 2.0); the wavefront integrator stays selectable.
     int integrator = p->integrator;
-    if (integrator == PTB_INTEGRATOR_AUTO) {
-        const bool wf = p->mode == PTB_MODE_PATH && small && bvh && (long long)fpb * n_local >= (1ll << 20);
-        integrator = wf ? PTB_INTEGRATOR_WAVEFRONT : PTB_INTEGRATOR_MEGAKERNEL;
-    }
+    if (integrator == PTB_INTEGRATOR_AUTO) integrator = PTB_INTEGRATOR_MEGAKERNEL;
 
     for (int f0 = 0; f0 < p->n_frames; f0 += fpb) {
         const int nb = (p->n_frames - f0 < fpb) ? p->n_frames - f0 : fpb;

@@ -1,5 +1,5 @@
 // lbvh.cuh -- BVH construction ON the GPU (BUILD-DEFINED): linear BVH by Morton order
-// (Karras 2012), widened on the device into the 128-byte 4-wide node format the traversal kernels use.
+// (Karras 2012), emitted directly in the 64-byte two-child node format the traversal kernels use.
 //
 //   k_lbvh_tri_bounds   per-triangle fp32 bounds + scene bounds (ordered-int atomicMin/Max)
 //   k_lbvh_morton       30-bit Morton code of the box centre, key = code << 32 | triangle index (unique keys)
@@ -8,8 +8,7 @@
 //                       range holds <= max_leaf triangles is emitted as a leaf reference (treelet collapse)
 //   k_lbvh_fit          bottom-up: one thread per sorted triangle climbs to the root; the second arrival at a
 //                       node (atomic flag) unions the two child boxes and goes on
-//   k_lbvh_widen        even-depth binary nodes -> 4-wide nodes over their grandchildren; pad, centre/half-extent
-//   k_lbvh_finish       write the precomputed-edge triangle records in sorted order
+//   k_lbvh_finish       pad the boxes, write the precomputed-edge triangle records in sorted order
 //
 // The result is deterministic (unique sort keys, exact min/max) and equivalent to the brute-force loop by the
 // same argument as the host SAH builder: every stored box is the exact bound of its triangles plus the pad.
@@ -153,59 +152,29 @@ __global__ void __launch_bounds__(256) k_lbvh_fit(const unsigned long long* keys
     atomicMax(max_depth, depth);
 }
 
-// Binary Karras nodes -> 4-wide nodes by depth parity: every internal node at EVEN depth becomes a wide node
-// whose slots are its grandchildren (a child that is a leaf reference keeps its own slot).  Wide node i lives at
-// the binary index i (odd-depth entries of the array stay unused).  Boxes: padded, centre/half-extent.
-__global__ void __launch_bounds__(256) k_lbvh_widen(const float4* bnodes, const int* parent, int n, float pad_rel,
-                                                    const int* scene_bounds, float4* wnodes) {
+__global__ void __launch_bounds__(256) k_lbvh_finish(const ptb_triangle* tris, const unsigned long long* keys, int n, float pad_rel,
+                                                     const int* scene_bounds, float4* nodes, float4* otris, int* tri_order) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    int dep = 0;
-    for (int p = parent[i]; p >= 0; p = parent[p >> 1]) ++dep;
-    if (dep & 1) return;
     const float dx = ordered_to_float(scene_bounds[3]) - ordered_to_float(scene_bounds[0]);
     const float dy = ordered_to_float(scene_bounds[4]) - ordered_to_float(scene_bounds[1]);
     const float dz = ordered_to_float(scene_bounds[5]) - ordered_to_float(scene_bounds[2]);
     const float pad = fmaxf(pad_rel, 0.0f) * sqrtf(dx * dx + dy * dy + dz * dz);
-    int refs[4] = {PTB_BVH_EMPTY, PTB_BVH_EMPTY, PTB_BVH_EMPTY, PTB_BVH_EMPTY};
-    float4 lo[4], hi[4];
-    int ns = 0;
-    const float4* me = bnodes + 4 * (size_t)i;
-    for (int side = 0; side < 2; ++side) {
-        const int ref = __float_as_int(me[side].w);
-        const float4 l = me[2 * side], h = me[2 * side + 1];
-        if (ref < 0) {  // leaf reference keeps its slot
-            refs[ns] = ref; lo[ns] = l; hi[ns] = h; ++ns;
-        } else {        // internal child at odd depth: take its two children
-            const float4* ch = bnodes + 4 * (size_t)ref;
-            refs[ns] = __float_as_int(ch[0].w); lo[ns] = ch[0]; hi[ns] = ch[1]; ++ns;
-            refs[ns] = __float_as_int(ch[1].w); lo[ns] = ch[2]; hi[ns] = ch[3]; ++ns;
-        }
+    if (i < n - 1) {
+        float4* nd = nodes + 4 * (size_t)i;
+        // padded [lo, hi] of each child -> centre / half-extent widened by two ulps (same rule as the host builder)
+        float4 a = nd[0], b = nd[1], c = nd[2], d = nd[3];
+        auto ce = [pad](float lo, float hi, float& cc, float& ee) {
+            lo -= pad; hi += pad;
+            cc = 0.5f * lo + 0.5f * hi;
+            const float h = 0.5f * hi - 0.5f * lo;
+            ee = h + 2.4e-7f * (fabsf(cc) + h);
+        };
+        float4 o0 = a, o1 = b, o2 = c, o3 = d;
+        ce(a.x, b.x, o0.x, o1.x); ce(a.y, b.y, o0.y, o1.y); ce(a.z, b.z, o0.z, o1.z);
+        ce(c.x, d.x, o2.x, o3.x); ce(c.y, d.y, o2.y, o3.y); ce(c.z, d.z, o2.z, o3.z);
+        o2.w = 0.f; o3.w = 0.f;
+        nd[0] = o0; nd[1] = o1; nd[2] = o2; nd[3] = o3;
     }
-    float4* out = wnodes + 8 * (size_t)i;
-    for (int k = 0; k < 4; ++k) {
-        float4 c = make_float4(0.f, 0.f, 0.f, 0.f), e = make_float4(-1e30f, -1e30f, -1e30f, 0.f);
-        if (k < ns) {
-            const float l3[3] = {lo[k].x - pad, lo[k].y - pad, lo[k].z - pad}, h3[3] = {hi[k].x + pad, hi[k].y + pad, hi[k].z + pad};
-            float cc[3], ee[3];
-            for (int a = 0; a < 3; ++a) {  // same widening rule as the host builder
-                cc[a] = 0.5f * l3[a] + 0.5f * h3[a];
-                const float hh = 0.5f * h3[a] - 0.5f * l3[a];
-                ee[a] = hh + 2.4e-7f * (fabsf(cc[a]) + hh);
-            }
-            c = make_float4(cc[0], cc[1], cc[2], 0.f);
-            e = make_float4(ee[0], ee[1], ee[2], 0.f);
-        }
-        out[2 * k] = c;
-        out[2 * k + 1] = e;
-    }
-    out[0].w = __int_as_float(refs[0]); out[1].w = __int_as_float(refs[1]);
-    out[2].w = __int_as_float(refs[2]); out[3].w = __int_as_float(refs[3]);
-}
-
-__global__ void __launch_bounds__(256) k_lbvh_finish(const ptb_triangle* tris, const unsigned long long* keys, int n,
-                                                     float4* otris, int* tri_order) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const int tri = (int)(keys[i] & 0xffffffffull);
         const float4* p = reinterpret_cast<const float4*>(tris + tri);
@@ -228,7 +197,7 @@ __global__ void __launch_bounds__(256) k_lbvh_finish(const ptb_triangle* tris, c
 static int build_lbvh_device(cudaStream_t st, const ptb_triangle* d_tris, int n, int max_leaf, float pad_rel, float4** d_nodes_out,
                              float4** d_otris_out, int** d_order_out, int* depth_out) {
     int rc = PTB_OK;
-    float4 *tlo = nullptr, *thi = nullptr, *nodes = nullptr, *otris = nullptr, *bnodes = nullptr;
+    float4 *tlo = nullptr, *thi = nullptr, *nodes = nullptr, *otris = nullptr;
     unsigned long long *keys = nullptr, *keys_sorted = nullptr;
     int *parent = nullptr, *flags = nullptr, *misc = nullptr, *order = nullptr;
     void* temp = nullptr;
@@ -245,8 +214,7 @@ static int build_lbvh_device(cudaStream_t st, const ptb_triangle* d_tris, int n,
     LBVH_TRY(cudaMalloc((void**)&parent, 4 * (size_t)(2 * n)));
     LBVH_TRY(cudaMalloc((void**)&flags, 4 * (size_t)n));
     LBVH_TRY(cudaMalloc((void**)&misc, 4 * 8));
-    LBVH_TRY(cudaMalloc((void**)&bnodes, 64 * (size_t)(n - 1)));
-    LBVH_TRY(cudaMalloc((void**)&nodes, 128 * (size_t)(n - 1)));
+    LBVH_TRY(cudaMalloc((void**)&nodes, 64 * (size_t)(n - 1)));
     LBVH_TRY(cudaMalloc((void**)&otris, 48 * (size_t)n));
     LBVH_TRY(cudaMalloc((void**)&order, 4 * (size_t)n));
     LBVH_TRY(cudaMemsetAsync(flags, 0, 4 * (size_t)n, st));
@@ -258,18 +226,17 @@ static int build_lbvh_device(cudaStream_t st, const ptb_triangle* d_tris, int n,
     LBVH_TRY(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, keys, keys_sorted, n, 0, 64, st));
     LBVH_TRY(cudaMalloc(&temp, temp_bytes));
     LBVH_TRY(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys, keys_sorted, n, 0, 64, st));
-    k_lbvh_topology<<<(n - 1 + 255) / 256, 256, 0, st>>>(keys_sorted, n, max_leaf, bnodes, parent);
-    k_lbvh_fit<<<grid_n, 256, 0, st>>>(keys_sorted, tlo, thi, n, bnodes, parent, flags, misc + 6);
-    k_lbvh_widen<<<(n - 1 + 255) / 256, 256, 0, st>>>(bnodes, parent, n, pad_rel, misc, nodes);
-    k_lbvh_finish<<<grid_n, 256, 0, st>>>(d_tris, keys_sorted, n, otris, order);
+    k_lbvh_topology<<<(n - 1 + 255) / 256, 256, 0, st>>>(keys_sorted, n, max_leaf, nodes, parent);
+    k_lbvh_fit<<<grid_n, 256, 0, st>>>(keys_sorted, tlo, thi, n, nodes, parent, flags, misc + 6);
+    k_lbvh_finish<<<grid_n, 256, 0, st>>>(d_tris, keys_sorted, n, pad_rel, misc, nodes, otris, order);
     LBVH_TRY(cudaGetLastError());
     LBVH_TRY(cudaMemcpyAsync(&depth, misc + 6, 4, cudaMemcpyDeviceToHost, st));
     LBVH_TRY(cudaStreamSynchronize(st));
-    *d_nodes_out = nodes; *d_otris_out = otris; *d_order_out = order; *depth_out = (depth + 1) / 2;  // wide levels
+    *d_nodes_out = nodes; *d_otris_out = otris; *d_order_out = order; *depth_out = depth;
     nodes = nullptr; otris = nullptr; order = nullptr;
 cleanup:
     for (void* p : {(void*)tlo, (void*)thi, (void*)keys, (void*)keys_sorted, (void*)parent, (void*)flags, (void*)misc, temp,
-                    (void*)bnodes, (void*)nodes, (void*)otris, (void*)order})
+                    (void*)nodes, (void*)otris, (void*)order})
         if (p) cudaFree(p);
     return rc;
 }

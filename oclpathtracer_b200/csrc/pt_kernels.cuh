@@ -42,7 +42,7 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
     Ctx c;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
     unsigned char* p = smem + 16;
-    const uint32_t node_bytes = BVH ? (uint32_t)sc.smem_nodes * 128u : 0u;
+    const uint32_t node_bytes = BVH ? (uint32_t)sc.smem_nodes * (SMALL ? 128u : 64u) : 0u;
     const uint32_t tri_bytes = SMALL ? (uint32_t)sc.n_tris * 48u : 0u;
     const uint32_t mat_bytes = SMALL ? (uint32_t)sc.n_mats * 32u : 0u;
     float4* s_nodes = reinterpret_cast<float4*>(p);
@@ -98,7 +98,7 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
 // host helper: bytes of dynamic shared memory for a launch
 static inline size_t scene_smem_bytes(const SceneDev& sc, bool bvh, bool small, int block, size_t scratch_per_thread = 0) {
     size_t b = 16;
-    if (bvh) b += (size_t)sc.smem_nodes * 128;
+    if (bvh) b += (size_t)sc.smem_nodes * (small ? 128 : 64);
     if (small) b += (size_t)sc.n_tris * 48 + (size_t)sc.n_mats * 32;
     if (bvh && !sc.lstack) b += (size_t)sc.stack_depth * block * 8;
     return b + scratch_per_thread * block;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(128) k_mega(const SceneDev sc, const RenderArg
 // slot from a global counter (one warp-aggregated atomicAdd per refill), so every warp iteration is one
 // path segment for (nearly) 32 live lanes.  Per-sample arithmetic is unchanged -> identical results.
 template <bool BVH, bool SMALL, bool STATS>
-__global__ void __launch_bounds__(128, 8) k_mega_path_regen(const SceneDev sc, const RenderArgs a,
+__global__ void __launch_bounds__(128) k_mega_path_regen(const SceneDev sc, const RenderArgs a,
                                                          unsigned long long* work_counter) {
     extern __shared__ __align__(16) unsigned char smem[];
     Ctx c = stage_scene<BVH, SMALL>(sc, smem);

@@ -236,7 +236,7 @@ struct ExtendStore : ExtendIO {
 };
 
 template <bool SMALL, bool STATS>
-__global__ void __launch_bounds__(128, 8) wf_extend_p(const SceneDev sc, const WfBuffers w, const int depth, const int qi,
+__global__ void __launch_bounds__(128) wf_extend_p(const SceneDev sc, const WfBuffers w, const int depth, const int qi,
                                                    unsigned long long* counters, const int refill_thr) {
     const unsigned int n = w.counts[depth];
     if (blockIdx.x * blockDim.x >= n) return;

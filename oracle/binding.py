@@ -24,7 +24,13 @@ TRIANGLE_DTYPE = np.dtype(
 MATERIAL_DTYPE = np.dtype(
     [("albedo", "<f4", 4), ("emissive", "<f4", 4), ("roughness", "<f4"), ("type", "<i4"), ("padding", "u1", 24)]
 )
-NODE_DTYPE = np.dtype(
+NODE_DTYPE = np.dtype(  # binary node, 64 bytes (ptb_bvh_node)
+    [
+        ("c0", "<f4", 3), ("child0", "<i4"), ("e0", "<f4", 3), ("child1", "<i4"),
+        ("c1", "<f4", 3), ("pad0", "<i4"), ("e1", "<f4", 3), ("pad1", "<i4"),
+    ]
+)
+NODE4_DTYPE = np.dtype(  # 4-wide node, 128 bytes (ptb_bvh_node4)
     [
         ("c0", "<f4", 3), ("child0", "<i4"), ("e0", "<f4", 3), ("child1", "<i4"),
         ("c1", "<f4", 3), ("child2", "<i4"), ("e1", "<f4", 3), ("child3", "<i4"),
@@ -39,13 +45,13 @@ STATS_DTYPE = np.dtype(
     ]
 )
 assert TRIANGLE_DTYPE.itemsize == 64 and MATERIAL_DTYPE.itemsize == 64
-assert NODE_DTYPE.itemsize == 128 and STATS_DTYPE.itemsize == 32
+assert NODE_DTYPE.itemsize == 64 and NODE4_DTYPE.itemsize == 128 and STATS_DTYPE.itemsize == 32
 
 
 class Bvh(C.Structure):
     _fields_ = [
         ("nodes", C.c_void_p), ("n_nodes", C.c_int32),
-        ("tri_order", C.c_void_p), ("n_tris", C.c_int32),
+        ("tri_order", C.c_void_p), ("n_tris", C.c_int32), ("width", C.c_int32),
     ]
 
 
@@ -159,10 +165,11 @@ def generate_ray(gi, gj, w, h, seed):
 
 
 def make_bvh(nodes, tri_order):
-    """nodes: NODE_DTYPE array; tri_order: int32 array.  Returns (Bvh, keepalive)."""
+    """nodes: NODE_DTYPE (binary) or NODE4_DTYPE (4-wide) array; tri_order: int32 array.  Returns (Bvh, keepalive)."""
     nodes = np.ascontiguousarray(nodes)
     order = np.ascontiguousarray(tri_order, np.int32)
-    b = Bvh(nodes.ctypes.data, len(nodes), order.ctypes.data, len(order))
+    width = {64: 2, 128: 4}[nodes.dtype.itemsize]
+    b = Bvh(nodes.ctypes.data, len(nodes), order.ctypes.data, len(order), width)
     return b, (nodes, order)
 
 

@@ -429,7 +429,7 @@ static inline int bvh_slab(const float c[3], const float e[3], const float invd[
  *  - pop: closest-hit entries whose stored entry distance exceeds best_t are discarded unvisited.         */
 #define ORA_STACK 256
 
-static int bvh_query(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, float tmax, int any_hit, qhit* h,
+static int bvh_query4(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, float tmax, int any_hit, qhit* h,
                      uint32_t* visits, qctr* c) {
     float invd[3] = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
     float ood[3] = {o.x * invd[0], o.y * invd[1], o.z * invd[2]};
@@ -444,7 +444,7 @@ static int bvh_query(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, f
     for (;;) {
         int descend = 0;
         if (cur >= 0) {
-            const ora_bvh_node* nd = &bvh->nodes[cur];
+            const ora_bvh_node4* nd = &((const ora_bvh_node4*)bvh->nodes)[cur];
             (*visits)++;
             c->nodes++;
             const float* cs[4] = {nd->c0, nd->c1, nd->c2, nd->c3};
@@ -510,6 +510,89 @@ static int bvh_query(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, f
             if (any_hit || stack_tn[sp] <= best_t) break;
         }
     }
+}
+
+/* BINARY tree (scenes traversed from L2/HBM): fetch the node (visits++), slab-test both child boxes against
+ * [0, best_t]; both hit -> descend into the nearer (child 1 only if tn1 < tn0), push the other with its entry
+ * distance; one hit -> descend.  Leaves, acceptance and pop as for the 4-wide tree.                        */
+static int bvh_query2(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, float tmax, int any_hit, qhit* h,
+                     uint32_t* visits, qctr* c) {
+    float invd[3] = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
+    float ood[3] = {o.x * invd[0], o.y * invd[1], o.z * invd[2]};
+    int32_t stack_ref[ORA_STACK];
+    float stack_tn[ORA_STACK];
+    int sp = 0;
+    float best_t = tmax;
+    int best_tri = -1;
+    float best_u = 0, best_v = 0;
+    int32_t cur = 0;
+    if (any_hit) c->any++; else c->closest++;
+    for (;;) {
+        if (cur == 0x7fffffff) {
+            /* empty child: nothing */
+        } else if (cur >= 0) {
+            const ora_bvh_node* nd = &((const ora_bvh_node*)bvh->nodes)[cur];
+            (*visits)++;
+            c->nodes++;
+            float tn0, tn1;
+            int h0 = nd->child0 != 0x7fffffff && bvh_slab(nd->c0, nd->e0, invd, ood, best_t, &tn0);
+            int h1 = nd->child1 != 0x7fffffff && bvh_slab(nd->c1, nd->e1, invd, ood, best_t, &tn1);
+            if (h0 && h1) {
+                if (tn1 < tn0) {
+                    stack_ref[sp] = nd->child0; stack_tn[sp] = tn0; sp++;
+                    cur = nd->child1;
+                } else {
+                    stack_ref[sp] = nd->child1; stack_tn[sp] = tn1; sp++;
+                    cur = nd->child0;
+                }
+                continue;
+            } else if (h0) {
+                cur = nd->child0;
+                continue;
+            } else if (h1) {
+                cur = nd->child1;
+                continue;
+            }
+        } else {
+            uint32_t code = (uint32_t)(~cur);
+            int first = (int)(code >> 3), count = (int)(code & 7u) + 1;
+            for (int k = first; k < first + count; k++) {
+                int idx = bvh->tri_order[k];
+                float t, u, v;
+                if (!mt_core(o, d, &tris[idx], &t, &u, &v, c)) continue;
+                if (any_hit) {
+                    if (t < best_t) {
+                        c->acc++;
+                        h->t = t; h->u = u; h->v = v; h->tri = idx;
+                        return 1;
+                    }
+                } else if (t < best_t || (t == best_t && best_tri >= 0 && idx < best_tri)) {
+                    c->acc++;
+                    best_t = t; best_u = u; best_v = v; best_tri = idx;
+                }
+            }
+        }
+        /* pop */
+        for (;;) {
+            if (sp == 0) {
+                if (best_tri >= 0 && !any_hit) {
+                    h->t = best_t; h->u = best_u; h->v = best_v; h->tri = best_tri;
+                    return 1;
+                }
+                h->tri = -1;
+                return 0;
+            }
+            sp--;
+            cur = stack_ref[sp];
+            if (stack_tn[sp] <= best_t) break;
+        }
+    }
+}
+
+static int bvh_query(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, float tmax, int any_hit, qhit* h,
+                     uint32_t* visits, qctr* c) {
+    if (bvh->width == 4) return bvh_query4(tris, bvh, o, d, tmax, any_hit, h, visits, c);
+    return bvh_query2(tris, bvh, o, d, tmax, any_hit, h, visits, c);
 }
 
 /* query context */

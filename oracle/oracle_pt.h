@@ -55,10 +55,21 @@ typedef struct ora_triangle {
 /* BUILD-DEFINED acceleration structure, consumed as DATA (built by the product's
  * host builder, validated structurally by tests): same byte layout as
  * include/SharedHeader.h:ptb_bvh_node.                                         */
-typedef struct ora_bvh_node { /* 4-wide, 128 bytes */
+typedef struct ora_bvh_node { /* binary, 64 bytes (include/SharedHeader.h: ptb_bvh_node) */
     float c0[3]; /* child-0 box centre      */
     int32_t child0;
     float e0[3]; /* child-0 box half-extent */
+    int32_t child1;
+    float c1[3];
+    int32_t pad0;
+    float e1[3];
+    int32_t pad1;
+} ora_bvh_node;
+
+typedef struct ora_bvh_node4 { /* 4-wide, 128 bytes (ptb_bvh_node4) */
+    float c0[3];
+    int32_t child0;
+    float e0[3];
     int32_t child1;
     float c1[3];
     int32_t child2;
@@ -72,13 +83,14 @@ typedef struct ora_bvh_node { /* 4-wide, 128 bytes */
     int32_t pad2;
     float e3[3];
     int32_t pad3;
-} ora_bvh_node;
+} ora_bvh_node4;
 
 typedef struct ora_bvh {
-    const ora_bvh_node* nodes;
+    const void* nodes; /* ora_bvh_node[n_nodes] when width == 2, ora_bvh_node4[n_nodes] when width == 4 */
     int32_t n_nodes;
     const int32_t* tri_order; /* BVH position -> index into the caller's triangle array */
     int32_t n_tris;
+    int32_t width;
 } ora_bvh;
 
 enum { ORA_MODE_PRIMARY = 0, ORA_MODE_AO = 1, ORA_MODE_DIRECT = 2, ORA_MODE_PATH = 3 };

@@ -86,7 +86,7 @@ def oracle_small():
     b = pt.build_bvh_host(tris)
     bvh, _keep = ob.make_bvh(b["nodes"], b["tri_order"])
     p1, ea, eb = ob.light_from_quad(tris, 5)
-    out = {"bvh_nodes": b["nodes"].view(np.uint8).reshape(-1, 128), "bvh_order": b["tri_order"]}
+    out = {"bvh_nodes": b["nodes"].view(np.uint8).reshape(-1, b["nodes"].dtype.itemsize), "bvh_order": b["tri_order"]}
     for name, mode in (("primary", 0), ("ao", 1), ("direct", 2), ("path", 3)):
         prm = ob.default_params(32, 32, n_frames=3, mode=mode, accum=ob.ACCUM_LINEAR, use_bvh=1, max_depth=8,
                                 light_p1=p1, light_ea=ea, light_eb=eb)

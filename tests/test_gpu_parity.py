@@ -267,8 +267,8 @@ def _tessellated_body(dev, pt, ob, cornell):
     bp = pt.bvh_params(smem_nodes=128)
     sc = dev.scene(big, mats, bp)
     info = sc.info()
-    assert info["n_nodes"] > info["smem_nodes"] == 128
-    dev.set_tuning(4, 128)  # stage the whole 128-node prefix (default cap is 32)
+    assert info["n_nodes"] > info["smem_nodes"] == 128 and info["width"] == 2
+    dev.set_tuning(4, 128)  # stage the whole 128-node prefix (default cap is 64)
     nodes, order = sc.bvh()
     bvh, _keep = ob.make_bvh(nodes, order)
     w, h = 64, 64
@@ -509,6 +509,7 @@ def test_launch_capture_and_replay(dev, pt, ob, cornell, tmp_path):
 def _check_tree(nodes, order, tris, pad_min):
     """every triangle reachable exactly once from the root; every child box contains its triangles (+pad)."""
     n = len(tris)
+    W = 4 if nodes.dtype.itemsize == 128 else 2
     tri_lo = np.minimum(np.minimum(tris["p1"], tris["p2"]), tris["p3"])[:, :3]
     tri_hi = np.maximum(np.maximum(tris["p1"], tris["p2"]), tris["p3"])[:, :3]
     covered = np.zeros(n, np.int32)
@@ -521,7 +522,7 @@ def _check_tree(nodes, order, tris, pad_min):
     while order_stack:
         ni = order_stack.pop()
         visit.append(ni)
-        for ch in (int(nodes[f"child{k}"][ni]) for k in range(4)):
+        for ch in (int(nodes[f"child{k}"][ni]) for k in range(W)):
             if ch >= 0 and ch != 0x7FFFFFFF:
                 order_stack.append(ch)
     assert len(set(visit)) == len(visit)
@@ -537,7 +538,7 @@ def _check_tree(nodes, order, tris, pad_min):
     for ni in reversed(visit):
         nd = nodes[ni]
         res = []
-        for k in range(4):
+        for k in range(W):
             ch, c, e = int(nd[f"child{k}"]), nd[f"c{k}"].astype(np.float64), nd[f"e{k}"].astype(np.float64)
             if ch == 0x7FFFFFFF:
                 assert (e < 0).all()
@@ -558,7 +559,7 @@ def test_gpu_lbvh_builder(dev, pt, ob, cornell, k, max_leaf):
     p1, ea, eb = pt.light_from_quad(tris, 5)
     sc = dev.scene(scene_tris, mats, pt.bvh_params(max_leaf=max_leaf), gpu_build=True)
     info = sc.info()
-    assert info["n_nodes"] == len(scene_tris) - 1 and info["smem_nodes"] == 1 and 1 <= info["depth"] <= 40
+    assert info["n_nodes"] == len(scene_tris) - 1 and info["smem_nodes"] == 1 and 1 <= info["depth"] <= 64 and info["width"] == 2
     nodes, order = sc.bvh()
     _check_tree(nodes, order, scene_tris, pad_min=5e-4)
     # deterministic: a second build gives the same bytes
@@ -569,7 +570,7 @@ def test_gpu_lbvh_builder(dev, pt, ob, cornell, k, max_leaf):
     st = [0]
     while st:
         i = st.pop(); live[i] = True
-        st += [int(nodes[f"child{k}"][i]) for k in range(4) if 0 <= nodes[f"child{k}"][i] != 0x7FFFFFFF]
+        st += [int(nodes[f"child{k}"][i]) for k in range(2) if 0 <= nodes[f"child{k}"][i] != 0x7FFFFFFF]
     assert nodes[live].tobytes() == n2[live].tobytes()
     sc2.close()
     o, d = _rays(30_000, 17)

@@ -25,7 +25,7 @@ def test_struct_sizes_match_reference_layout(pt):
     assert pt.TRIANGLE_DTYPE.itemsize == 64 and pt.MATERIAL_DTYPE.itemsize == 64
     assert pt.TRIANGLE_DTYPE.fields["id"][1] == 48
     assert pt.MATERIAL_DTYPE.fields["roughness"][1] == 32 and pt.MATERIAL_DTYPE.fields["type"][1] == 36
-    assert pt.NODE_DTYPE.itemsize == 128 and pt.BVH_TRI_DTYPE.itemsize == 48 and pt.STATS_DTYPE.itemsize == 32
+    assert pt.NODE_DTYPE.itemsize == 64 and pt.NODE4_DTYPE.itemsize == 128 and pt.BVH_TRI_DTYPE.itemsize == 48 and pt.STATS_DTYPE.itemsize == 32
     assert C.sizeof(pt.RenderParams) % 4 == 0 and C.sizeof(pt.Counters) == 64
 
 
@@ -77,7 +77,7 @@ def _validate_bvh(pt, tris, b, pad_min=0.0):
         seen_nodes[ref] = True
         nd = nodes[ref]
         lo_all, hi_all, used = [], [], 0
-        for k in range(4):  # 4-wide node: box k = [c_k - e_k, c_k + e_k]
+        for k in range(b["width"]):  # box k = [c_k - e_k, c_k + e_k]
             ch = int(nd[f"child{k}"])
             c, e = nd[f"c{k}"].astype(np.float64), nd[f"e{k}"].astype(np.float64)
             if ch == 0x7FFFFFFF:
@@ -99,30 +99,36 @@ def _validate_bvh(pt, tris, b, pad_min=0.0):
 def test_bvh_structure_cornell(pt, cornell):
     tris, _ = cornell
     b = pt.build_bvh_host(tris)
-    assert b["smem_nodes"] == len(b["nodes"]) <= 17 and 1 <= b["depth"] <= 8
+    assert b["width"] == 4 and b["smem_nodes"] == len(b["nodes"]) <= 17 and 1 <= b["depth"] <= 8
     _validate_bvh(pt, tris, b, pad_min=5e-4)  # default pad = 1e-4 * diagonal(9.6) ~ 9.6e-4
+    b2 = pt.build_bvh_host(tris, width=2)
+    assert b2["smem_nodes"] == len(b2["nodes"]) <= 35 and 1 <= b2["depth"] <= 12
+    np.testing.assert_array_equal(b2["tri_order"], b["tri_order"])  # same tree, collapsed
+    _validate_bvh(pt, tris, b2, pad_min=5e-4)
 
 
-@pytest.mark.parametrize("k,max_leaf", [(4, 4), (12, 2), (9, 8)])
-def test_bvh_structure_tessellated(pt, cornell, k, max_leaf):
+@pytest.mark.parametrize("k,max_leaf,width", [(4, 4, 2), (4, 4, 4), (12, 2, 2), (9, 8, 2), (7, 3, 4)])
+def test_bvh_structure_tessellated(pt, cornell, k, max_leaf, width):
     tris, _ = cornell
     big = pt.tessellate(tris, k)
-    b = pt.build_bvh_host(big, pt.bvh_params(max_leaf=max_leaf, smem_nodes=64))
+    b = pt.build_bvh_host(big, pt.bvh_params(max_leaf=max_leaf, smem_nodes=64), width=width)
     assert b["smem_nodes"] == min(64, len(b["nodes"]))
     _validate_bvh(pt, big, b, pad_min=5e-4)
     # breadth-first prefix: children of early nodes come later, prefix is closed under "parent of"
-    kids = np.concatenate([b["nodes"][f"child{k}"] for k in range(4)])
+    kids = np.concatenate([b["nodes"][f"child{k}"] for k in range(width)])
     assert (kids[(kids >= 0) & (kids != 0x7FFFFFFF)] > 0).all()
 
 
 def test_bvh_degenerate_inputs(pt, cornell):
     tris, _ = cornell
-    one = pt.build_bvh_host(tris[:1])
+    one = pt.build_bvh_host(tris[:1], width=4)
     assert len(one["nodes"]) == 1 and one["nodes"]["child0"][0] == one["nodes"]["child1"][0] < 0
     assert one["nodes"]["child2"][0] == one["nodes"]["child3"][0] == 0x7FFFFFFF
     same = np.repeat(tris[:1], 9)  # identical centroids: no bin separates them -> median split fallback
-    b = pt.build_bvh_host(same)
-    _validate_bvh(pt, same, b)
+    for width in (2, 4):
+        _validate_bvh(pt, same, pt.build_bvh_host(same, width=width))
+    with pytest.raises(pt.PtbError, match="2048"):
+        pt.build_bvh_host(pt.tessellate(tris, 12), width=4)
     bad = tris[:2].copy()
     bad["p1"][0, 0] = np.nan
     with pytest.raises(pt.PtbError, match="non-finite"):

@@ -121,9 +121,11 @@ def test_bvh_equals_brute_force(ob, cornell, cornell_bvh, mode):
     assert cb["nodes"] > 0 and cb["tri_tests"] < ca["tri_tests"]
 
 
-def test_trace_random_rays_brute_vs_bvh(ob, cornell, cornell_bvh):
+@pytest.mark.parametrize("width", [4, 2])
+def test_trace_random_rays_brute_vs_bvh(pt, ob, cornell, width):
     tris, _ = cornell
-    _, bvh, _ = cornell_bvh
+    b = pt.build_bvh_host(tris, width=width)
+    bvh, _keep = ob.make_bvh(b["nodes"], b["tri_order"])
     rng = np.random.default_rng(3)
     n = 200_000
     o = rng.uniform([-2.7, 0.05, -5.5], [2.7, 5.4, 3.0], (n, 3)).astype(np.float32)
