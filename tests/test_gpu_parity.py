@@ -605,3 +605,50 @@ def test_reference_device_tests_over_shim():
     r = subprocess.run([exe, SCENE], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("[       OK ]") == 7
+
+
+def test_c5_two_million_triangles_properties(dev, pt, ob, cornell):
+    """configs[4] scene at full size (18 quads x 236^2 x 2 = 2,005,056 triangles), reduced image.
+    Size-independent properties: radiance does not depend on the acceleration structure (host SAH tree ==
+    device LBVH tree == megakernel == wavefront, bit for bit), sampled hit ids equal the reference's
+    brute-force loop over all 2M triangles, and a sampled set of pixels equals the CPU oracle on the SAH tree."""
+    tris, mats = cornell
+    big = pt.tessellate(tris, 236)
+    assert len(big) == 2_005_056
+    p1, ea, eb = pt.light_from_quad(tris, 5)
+    w, h = 640, 360
+    kw = dict(width=w, height=h, n_frames=1, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR, max_depth=8,
+              light_p1=p1, light_ea=ea, light_eb=eb)
+    frames = {}
+    sah = dev.scene(big, mats)
+    assert sah.info()["width"] == 2 and sah.info()["n_nodes"] > 500_000
+    for name, integ in (("sah_mega", pt.INTEGRATOR_MEGAKERNEL), ("sah_wave", pt.INTEGRATOR_WAVEFRONT)):
+        frame = dev.buffer(w * h * 16)
+        ctr = dev.render(sah, pt.default_params(integrator=integ, **kw), frame, None, want_counters=True)
+        frames[name] = (frame.read(np.uint32).tobytes(), ctr["rays_closest"])
+        frame.close()
+    # sampled ground truth: the reference's brute-force loop (on the GPU: 2M Moller-Trumbore tests per ray)
+    o, d = _rays(1500, 23)
+    g = dev.trace(sah, o, d, np.float32(1e20), accel=pt.ACCEL_BVH)
+    r = dev.trace(sah, o, d, np.float32(1e20), accel=pt.ACCEL_BRUTE)
+    for f in ("tri", "t", "u", "v"):
+        np.testing.assert_array_equal(bits(g[f]), bits(r[f]))
+    assert (r["tests"] == len(big)).all() and g["tests"].max() < 200
+    # a shard of the image against the CPU oracle walking the same tree
+    nodes, order = sah.bvh()
+    bvh, _keep = ob.make_bvh(nodes, order)
+    shard = dict(shard_index=3, shard_count=60, shard_block=64)
+    fbuf = dev.buffer(pt.local_pixels(pt.default_params(**kw, **shard)) * 16)
+    dev.render(sah, pt.default_params(**kw, **shard), fbuf)
+    got = fbuf.read(np.float32).reshape(-1, 4)
+    fbuf.close()
+    okw = dict(n_frames=1, mode=3, accum=1, max_depth=8, use_bvh=1, light_p1=p1, light_ea=ea, light_eb=eb, **shard)
+    want, _, _ = ob.render(ob.default_params(w, h, **okw), big, mats, bvh=bvh)
+    np.testing.assert_array_equal(bits(got), bits(want))
+    sah.close()
+    lb = dev.scene(big, mats, gpu_build=True)
+    frame = dev.buffer(w * h * 16)
+    ctr = dev.render(lb, pt.default_params(integrator=pt.INTEGRATOR_MEGAKERNEL, **kw), frame, None, want_counters=True)
+    frames["lbvh_mega"] = (frame.read(np.uint32).tobytes(), ctr["rays_closest"])
+    frame.close(); lb.close()
+    assert frames["sah_mega"] == frames["sah_wave"] == frames["lbvh_mega"]
