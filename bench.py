@@ -166,7 +166,8 @@ def cpu_reference(wl, seconds_budget=12.0, sample_px=None, max_frames=8):
     """Times the oracle's reference-faithful brute-force path (oracle/: the only CPU code bench.py runs).
 
     The reference has no CPU executor of its own (ADL's DeviceHost cannot launch kernels, SURVEY.md
-    section 0), and its OpenCL kernel cannot be built into oracle/_ref, so kind = "port".
+    section 0): oracle/_ref/adlTest64 is the genuine test program but it needs an OpenCL *GPU* platform
+    (measured once on the B200: profiles/reference_opencl_r01/), so the CPU arm is the port, kind = "port".
     """
     from oracle import binding as ob
 
