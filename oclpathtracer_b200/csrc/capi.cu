@@ -58,10 +58,11 @@ struct ptb_device {
     ptb_buffer* host_tris = nullptr; ptb_buffer* host_mats = nullptr;
     void* pinned = nullptr; size_t pinned_bytes = 0;  // staging of the scene records
     cudaStream_t copy_stream = nullptr;               // D2H of finished frames overlaps the next render
+    cudaStream_t up_stream = nullptr;                 // H2D of the caller's records, off the render stream's critical path
     struct HostSlot {
         ptb_buffer* frame = nullptr; ptb_buffer* stats = nullptr;
         void* pin = nullptr; size_t pin_bytes = 0;    // staging when the caller's buffers are pageable
-        cudaEvent_t ev_render = nullptr, ev_done = nullptr;
+        cudaEvent_t ev_render = nullptr, ev_done = nullptr, ev_up = nullptr;
         bool busy = false;
         float* out = nullptr; ptb_pixel_stats* out_stats = nullptr;
         size_t fb = 0, sb = 0;
@@ -199,6 +200,7 @@ extern "C" int ptb_device_destroy(ptb_device* dev) {
     set_device(dev);
     cudaStreamSynchronize(dev->stream);
     if (dev->copy_stream) cudaStreamSynchronize(dev->copy_stream);
+    if (dev->up_stream) cudaStreamSynchronize(dev->up_stream);
     if (dev->host_scene) ptb_scene_destroy(dev->host_scene);
     for (auto& sl : dev->slots) {
         if (sl.frame) ptb_buffer_destroy(sl.frame);
@@ -206,8 +208,10 @@ extern "C" int ptb_device_destroy(ptb_device* dev) {
         if (sl.pin) cudaFreeHost(sl.pin);
         if (sl.ev_render) cudaEventDestroy(sl.ev_render);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        if (sl.ev_up) cudaEventDestroy(sl.ev_up);
     }
     if (dev->copy_stream) cudaStreamDestroy(dev->copy_stream);
+    if (dev->up_stream) cudaStreamDestroy(dev->up_stream);
     for (ptb_buffer* b : {dev->host_tris, dev->host_mats})
         if (b) ptb_buffer_destroy(b);
     for (auto& kv : dev->kernels) {
@@ -820,7 +824,9 @@ extern "C" int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, 
     if (sl.busy) return fail(PTB_E_INVALID, "ptb_render_host_async: more than two jobs in flight; wait for the older one first");
     int rc;
     if (!dev->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
+    if (!dev->up_stream) CU_TRY(cudaStreamCreateWithFlags(&dev->up_stream, cudaStreamNonBlocking));
     if (!sl.ev_render) {
+        CU_TRY(cudaEventCreateWithFlags(&sl.ev_up, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&sl.ev_render, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
     }
@@ -836,20 +842,26 @@ extern "C" int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, 
     const void* src_m = mats;
     if (!is_pinned(tris) || !is_pinned(mats)) {  // pageable records go through pinned staging
         if (dev->pinned_bytes < tb + mb) {
-            CU_TRY(cudaStreamSynchronize(dev->stream));
+            CU_TRY(cudaStreamSynchronize(dev->up_stream));
             if (dev->pinned) cudaFreeHost(dev->pinned);
             dev->pinned = nullptr; dev->pinned_bytes = 0;
             CU_TRY(cudaMallocHost(&dev->pinned, tb + mb));
             dev->pinned_bytes = tb + mb;
         } else {
-            CU_TRY(cudaStreamSynchronize(dev->stream));  // the previous upload must have left the staging area
+            CU_TRY(cudaStreamSynchronize(dev->up_stream));  // the previous upload must have left the staging area
         }
         std::memcpy(dev->pinned, tris, tb);
         std::memcpy(static_cast<char*>(dev->pinned) + tb, mats, mb);
         src_t = dev->pinned;
         src_m = static_cast<char*>(dev->pinned) + tb;
     }
-    if ((rc = ptb_buffer_write(dev->host_tris, src_t, tb, 0)) || (rc = ptb_buffer_write(dev->host_mats, src_m, mb, 0))) return rc;
+    // The device copies of the records are the caller-visible upload (and what a device-side rebuild would read); the
+    // render itself reads the resident scene, so the copies run on their own stream and only the job's completion
+    // event waits for them.
+    CU_TRY(cudaMemcpyAsync(dev->host_tris->d_ptr, src_t, tb, cudaMemcpyHostToDevice, dev->up_stream));
+    CU_TRY(cudaMemcpyAsync(dev->host_mats->d_ptr, src_m, mb, cudaMemcpyHostToDevice, dev->up_stream));
+    dev->host_tris->version++; dev->host_mats->version++;
+    CU_TRY(cudaEventRecord(sl.ev_up, dev->up_stream));
     if (scene_changed) {
         if (dev->host_scene) ptb_scene_destroy(dev->host_scene);
         dev->host_scene = nullptr;
@@ -880,6 +892,7 @@ extern "C" int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, 
     char* pin = static_cast<char*>(sl.pin);
     CU_TRY(cudaMemcpyAsync(sl.direct_frame ? (void*)out_rgba : (void*)pin, sl.frame->d_ptr, fb, cudaMemcpyDeviceToHost, dev->copy_stream));
     if (sb) CU_TRY(cudaMemcpyAsync(sl.direct_stats ? (void*)out_stats : (void*)(pin + fb), sl.stats->d_ptr, sb, cudaMemcpyDeviceToHost, dev->copy_stream));
+    CU_TRY(cudaStreamWaitEvent(dev->copy_stream, sl.ev_up, 0));
     CU_TRY(cudaEventRecord(sl.ev_done, dev->copy_stream));
     sl.busy = true; sl.out = out_rgba; sl.out_stats = out_stats; sl.fb = fb; sl.sb = sb;
     ptb_job* job = new ptb_job{dev, si, dev->jobs_submitted};
