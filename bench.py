@@ -162,7 +162,7 @@ def peaks():
 # reference arm: the reference's algorithm (brute-force GenerateColors restatement) on the host cores
 # ------------------------------------------------------------------------------------------------------
 
-def cpu_reference(wl, seconds_budget=12.0, sample_px=None, max_frames=8):
+def cpu_reference(wl, seconds_budget=12.0, sample_px=None, max_frames=8, n_threads=0):
     """Times the oracle's reference-faithful brute-force path (oracle/: the only CPU code bench.py runs).
 
     The reference has no CPU executor of its own (ADL's DeviceHost cannot launch kernels, SURVEY.md
@@ -179,7 +179,7 @@ def cpu_reference(wl, seconds_budget=12.0, sample_px=None, max_frames=8):
     if sample_px is not None:  # bounded sample: a centred crop is not expressible, so shrink the image
         s = (sample_px / float(w * h)) ** 0.5
         w, h = max(16, int(w * s) // 16 * 16), max(16, int(h * s) // 16 * 16)
-    kw = dict(mode=wl["mode"], accum=ob.ACCUM_LINEAR, use_bvh=0, light_p1=p1, light_ea=ea, light_eb=eb)
+    kw = dict(mode=wl["mode"], accum=ob.ACCUM_LINEAR, use_bvh=0, light_p1=p1, light_ea=ea, light_eb=eb, n_threads=n_threads)
     if "ao_samples" in wl:
         kw["ao_samples"] = wl["ao_samples"]
     if "max_depth" in wl:
@@ -192,7 +192,7 @@ def cpu_reference(wl, seconds_budget=12.0, sample_px=None, max_frames=8):
         t_total += time.perf_counter() - t0
         rays += ctr["rays_closest"] + ctr["rays_any"]
         frames += 1
-    return {"value": rays / t_total / 1e6, "unit": "Mrays/s", "cores": ob.max_threads(), "kind": "port",
+    return {"value": rays / t_total / 1e6, "unit": "Mrays/s", "cores": n_threads or ob.max_threads(), "kind": "port",
             "sample": f"{frames} frame(s) of {w}x{h} ({rays} rays, {t_total:.2f} s), brute force over {len(tris)} triangles as the reference kernel",
             "seconds": t_total, "rays": rays, "frames": frames, "wh": [w, h]}
 
@@ -415,6 +415,13 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(wl, seconds_budget=12.0, sample_px=None if not wl.get("tess") else 16 * 16, max_frames=64)
+        one = cpu_reference(wl, seconds_budget=3.0, sample_px=256 * 256 if not wl.get("tess") else 8 * 8, max_frames=16, n_threads=1)
+        cpu["single_thread"] = {"value": one["value"], "unit": "Mrays/s", "cores": 1, "sample": one["sample"]}
+        ref_cmp = os.path.join(ROOT, "profiles", "reference_opencl_r01", "compare.json")
+        if os.path.exists(ref_cmp):  # recorded once, not re-measured here: the unmodified reference on this GPU via OpenCL
+            cpu["reference_opencl_on_b200"] = {"raycast_10000_frames_512x512_s": 357.4, "same_flow_through_libptb200_s": 5.0,
+                                               "image_rrmse": json.load(open(ref_cmp))["rrmse"],
+                                               "source": "profiles/reference_opencl_r01 (tools/run_reference_opencl.sh)"}
         from oracle import binding as ob
         # stage counts of the BVH path at reduced size -> fp32 lane-ops per ray (SURVEY 8d formula)
         otris, omats = ob.load_model(SCENE)
