@@ -84,7 +84,12 @@ size_t ptb_buffer_size(ptb_buffer* buf);
  * ("../test/ClKernels/GenerateColors") -- only its basename is matched.        */
 int ptb_kernel_get(ptb_device* dev, const char* file_name, const char* func_name, ptb_kernel** out);
 /* the reference's compile-time #defines (GenerateColors.cl:5-6) as run-time
- * options: "NUM_TRIANGLES" (36), "BOUNCES" (16), "ACCEL" (PTB_ACCEL_*)         */
+ * options: "NUM_TRIANGLES" (36), "BOUNCES" (16), "ACCEL" (PTB_ACCEL_*),
+ * "INTEGRATOR" (PTB_INTEGRATOR_*), and "FRAME_AHEAD" (1): when the caller steps
+ * through consecutive frame indices (the loop at RaytraceTest.cpp:248-262) the
+ * samples of the following frames are traced together in one launch that fills
+ * the GPU and each ptb_launch1d folds its own frame into the framebuffer --
+ * bit-identical to FRAME_AHEAD 0 (one integrator launch per call).            */
 int ptb_kernel_set_int(ptb_kernel* k, const char* name, int value);
 /* Launcher::setBuffers + setConst + launch1D  Adl/AdlKernel.h:166-184,
  * Adl/AdlKernel.inl:179-184, Adl/CL/AdlKernelUtilsCL.cpp:399-500.  Positional:

@@ -97,6 +97,13 @@ struct ptb_kernel {
     ptb_scene* scene = nullptr;
     const ptb_buffer* key_t = nullptr; const ptb_buffer* key_m = nullptr;
     uint64_t ver_t = 0, ver_m = 0, hash = 0;
+    // frame-ahead batch of the progressive loop (ptb_launch1d): samples of frames [ahead_first, ahead_first+ahead_count)
+    // already traced for (ahead_w x ahead_h, ahead_cfg); consumed one resolve per launch
+    void* ahead = nullptr; size_t ahead_bytes = 0;
+    int ahead_first = 0, ahead_count = 0, ahead_w = 0, ahead_h = 0;
+    int ahead_cfg[3] = {0, 0, 0};
+    int last_frame = -2, streak = 0;
+    int frame_ahead = 1;  // ptb_kernel_set_int(k, "FRAME_AHEAD", 0) restores one integrator launch per ptb_launch1d
 };
 
 struct ptb_scene {
@@ -216,6 +223,7 @@ extern "C" int ptb_device_destroy(ptb_device* dev) {
         if (b) ptb_buffer_destroy(b);
     for (auto& kv : dev->kernels) {
         if (kv.second->scene) ptb_scene_destroy(kv.second->scene);
+        if (kv.second->ahead) cudaFree(kv.second->ahead);
         delete kv.second;
     }
     if (dev->samples) cudaFree(dev->samples);
@@ -626,15 +634,19 @@ static int validate(const ptb_render_params* p) {
     return PTB_OK;
 }
 
+// `ext_samples` + `phase` split one call for the frame-ahead batching of ptb_launch1d: PHASE_TRACE writes the samples of
+// all n_frames into ext_samples and stops; PHASE_RESOLVE folds n_frames already-traced frames from ext_samples into d_frame.
+enum { PHASE_BOTH = 0, PHASE_TRACE = 1, PHASE_RESOLVE = 2 };
 static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_params* p, float4* d_frame, size_t frame_bytes,
-                       ptb_pixel_stats* d_stats, size_t stats_bytes, ptb_counters* counters) {
-    if (!dev || !scene || !d_frame) return fail(PTB_E_INVALID, "ptb_render: null argument");
+                       ptb_pixel_stats* d_stats, size_t stats_bytes, ptb_counters* counters, float4* ext_samples = nullptr,
+                       int phase = PHASE_BOTH) {
+    if (!dev || !scene || (!d_frame && phase != PHASE_TRACE)) return fail(PTB_E_INVALID, "ptb_render: null argument");
     if (int rc = validate(p)) return rc;
     if (scene->dev != dev) return fail(PTB_E_INVALID, "ptb_render: scene belongs to another device");
     if (set_device(dev)) return PTB_E_CUDA;
     const int n_local = ptb_render_local_pixels(p);
     if (n_local <= 0) return fail(PTB_E_INVALID, "ptb_render: shard owns no pixels");
-    if (frame_bytes < size_t(n_local) * 16) return fail(PTB_E_INVALID, "ptb_render: frame buffer too small (%zu < %zu)", frame_bytes, size_t(n_local) * 16);
+    if (phase != PHASE_TRACE && frame_bytes < size_t(n_local) * 16) return fail(PTB_E_INVALID, "ptb_render: frame buffer too small (%zu < %zu)", frame_bytes, size_t(n_local) * 16);
     if (d_stats && stats_bytes < size_t(n_local) * sizeof(ptb_pixel_stats)) return fail(PTB_E_INVALID, "ptb_render: stats buffer too small");
     if (p->mode == PTB_MODE_DIRECT && (p->light_quad < 0 || p->light_quad >= scene->n_mats))
         return fail(PTB_E_INVALID, "ptb_render: light_quad %d out of range", p->light_quad);
@@ -652,7 +664,8 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
     }
     if (fpb > p->n_frames) fpb = p->n_frames;
     if (fpb < 1) fpb = 1;
-    if (int rc = ensure(&dev->samples, &dev->samples_bytes, size_t(fpb) * n_local * 16)) return rc;
+    if (ext_samples) fpb = p->n_frames;  // the caller sized ext_samples for the whole range
+    else if (int rc = ensure(&dev->samples, &dev->samples_bytes, size_t(fpb) * n_local * 16)) return rc;
     if (p->accum == PTB_ACCUM_LINEAR)
         if (int rc = ensure(&dev->sum, &dev->sum_bytes, size_t(n_local) * 16)) return rc;
     CU_TRY(cudaMemsetAsync(dev->counters, 0, sizeof(unsigned long long) * 64, dev->stream));
@@ -670,7 +683,7 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
         if (int rc = ptb_light_from_quad(scene->host_tris.data(), scene->n_tris, p->light_quad, a.light_p1, a.light_ea, a.light_eb)) return rc;
     }
     a.shard.index = p->shard_index; a.shard.count = p->shard_count < 1 ? 1 : p->shard_count; a.shard.block = p->shard_block < 1 ? 1 : p->shard_block;
-    a.samples = static_cast<float4*>(dev->samples);
+    a.samples = ext_samples ? ext_samples : static_cast<float4*>(dev->samples);
     a.stats = stats ? d_stats : nullptr;
     a.stats_frame = p->first_frame + p->n_frames - 1;
     a.counters = dev->counters;
@@ -699,7 +712,8 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
             dev->ev_used += 3;
             CU_TRY(cudaEventRecord(ev[0], dev->stream));
         }
-        if (integrator == PTB_INTEGRATOR_WAVEFRONT) {
+        if (phase == PHASE_RESOLVE) {
+        } else if (integrator == PTB_INTEGRATOR_WAVEFRONT) {
             if (int rc = ptd::wavefront_render(dev->stream, &dev->wf, &dev->wf_bytes, dev->counters, p->mode, sc, a, bvh, small, stats,
                                                dev->prop.multiProcessorCount, &dev->kernel_launches))
                 return rc;
@@ -708,7 +722,8 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
             dev->kernel_launches += 1;
         }
         if (ev) CU_TRY(cudaEventRecord(ev[1], dev->stream));
-        dev->integrator_launch_batches++;
+        if (phase != PHASE_RESOLVE) dev->integrator_launch_batches++;
+        if (phase == PHASE_TRACE) continue;
         ptd::ResolveArgs r;
         r.samples = a.samples; r.n_local = n_local; r.frames_in_batch = nb; r.first_frame = a.first_frame;
         r.accum = p->accum; r.first_batch = f0 == 0; r.last_batch = f0 + nb >= p->n_frames;
@@ -957,6 +972,7 @@ extern "C" int ptb_kernel_set_int(ptb_kernel* k, const char* name, int value) {
     else if (!std::strcmp(name, "BOUNCES")) { if (value < 1) return fail(PTB_E_INVALID, "BOUNCES must be >= 1"); k->bounces = value; }
     else if (!std::strcmp(name, "ACCEL")) k->accel = value;
     else if (!std::strcmp(name, "INTEGRATOR")) k->integrator = value;
+    else if (!std::strcmp(name, "FRAME_AHEAD")) { k->frame_ahead = value != 0; k->ahead_count = 0; }
     else return fail(PTB_E_NOTFOUND, "ptb_kernel_set_int: unknown option %s", name);
     return PTB_OK;
 }
@@ -979,6 +995,7 @@ extern "C" int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* b
     if (set_device(dev)) return PTB_E_CUDA;
     // resident scene for the bound buffers; rebuilt when their contents changed
     const bool tracked = tb->owned && mb->owned;
+    bool scene_rebuilt = false;
     if (!k->scene || !tracked || k->key_t != tb || k->key_m != mb || k->ver_t != tb->version || k->ver_m != mb->version) {
         std::vector<ptb_triangle> ht(nt);
         CU_TRY(cudaMemcpyAsync(ht.data(), tb->d_ptr, size_t(nt) * sizeof(ptb_triangle), cudaMemcpyDeviceToHost, dev->stream));
@@ -997,6 +1014,7 @@ extern "C" int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* b
             k->scene = nullptr;
             if (int rc = ptb_scene_create(dev, ht.data(), nt, hm.data(), nm, nullptr, &k->scene)) return rc;
             k->hash = h;
+            scene_rebuilt = true;
         }
         k->key_t = tb; k->key_m = mb; k->ver_t = tb->version; k->ver_m = mb->version;
     }
@@ -1006,7 +1024,45 @@ extern "C" int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* b
     p.first_frame = res.z; p.n_frames = 1;  // RaytraceTest.cpp:252-253: one launch = one frame index
     p.mode = PTB_MODE_PATH; p.accum = PTB_ACCUM_REFERENCE;
     p.max_depth = k->bounces; p.accel = k->accel; p.integrator = k->integrator;
-    return render_impl(dev, k->scene, &p, static_cast<float4*>(fb->d_ptr), fb->bytes, nullptr, 0, nullptr);
+    float4* d_fb = static_cast<float4*>(fb->d_ptr);
+
+    // Frame-ahead batching.  One 512x512 frame is under one wave of threads, so a launch-per-frame loop runs at the
+    // latency of its longest path.  A sample depends only on (scene, W, H, pixel, frame) -- not on the framebuffer --
+    // so once the caller is seen stepping through consecutive frame indices (the progressive loop,
+    // RaytraceTest.cpp:248-262), the samples of the next frames are traced together in one full-GPU launch and each
+    // later launch only folds its own frame into the caller's buffer.  Results are bit-identical to the
+    // frame-by-frame path (same per-sample arithmetic, same ordered running mean); anything that could change a
+    // sample (buffers rewritten, NUM_TRIANGLES/BOUNCES/ACCEL/INTEGRATOR, image size) discards the batch.
+    const int z = res.z;
+    const int cfg[3] = {k->bounces, k->accel, k->integrator};
+    const bool same_cfg = k->ahead_w == res.x && k->ahead_h == res.y && !std::memcmp(cfg, k->ahead_cfg, sizeof cfg);
+    if (!same_cfg || scene_rebuilt) k->ahead_count = 0;
+    k->streak = (z == k->last_frame + 1 && same_cfg && !scene_rebuilt) ? k->streak + 1 : 0;
+    k->last_frame = z;
+    k->ahead_w = res.x; k->ahead_h = res.y; std::memcpy(k->ahead_cfg, cfg, sizeof cfg);
+    const bool speculate = k->frame_ahead != 0;
+    if (speculate && !(k->ahead_count > 0 && z >= k->ahead_first && z < k->ahead_first + k->ahead_count) && k->streak >= 1) {
+        const long long target = 4ll << 20;  // sample slots in flight, as ptb_render's frames_per_batch default
+        int want = (int)((target + n_threads - 1) / n_threads);
+        const int ramp = k->streak >= 5 ? want : (1 << k->streak);  // 2, 4, 8, 16 ... so a short sequence wastes little
+        if (want > ramp) want = ramp;
+        if (want > 0x7fffffff - z) want = 0x7fffffff - z;
+        if (want >= 2) {
+            if (int rc = ensure(&k->ahead, &k->ahead_bytes, size_t(want) * size_t(n_threads) * 16)) return rc;
+            ptb_render_params pb = p;
+            pb.n_frames = want;
+            if (int rc = render_impl(dev, k->scene, &pb, nullptr, 0, nullptr, 0, nullptr, static_cast<float4*>(k->ahead), PHASE_TRACE)) {
+                k->ahead_count = 0;
+                return rc;
+            }
+            k->ahead_first = z; k->ahead_count = want;
+        }
+    }
+    if (speculate && k->ahead_count > 0 && z >= k->ahead_first && z < k->ahead_first + k->ahead_count) {
+        float4* smp = static_cast<float4*>(k->ahead) + size_t(z - k->ahead_first) * size_t(n_threads);
+        return render_impl(dev, k->scene, &p, d_fb, fb->bytes, nullptr, 0, nullptr, smp, PHASE_RESOLVE);
+    }
+    return render_impl(dev, k->scene, &p, d_fb, fb->bytes, nullptr, 0, nullptr);
 }
 
 // ---- launch capture / replay (Launcher::serializeToFile / deserializeFromFile) ---------------------------------

@@ -12,15 +12,50 @@
 // handles / zero sizes and the message is available from ptb_last_error().
 #pragma once
 
+// standard headers the reference's Adl.h / AdlKernel.h make visible to their includers
+#include <assert.h>
+#include <limits.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
+#include <map>
+#include <string>
 
 #include "ptb200.h"
+
+// The reference's flow spells its records with OpenCL host types (clew.h, pulled in by the reference's Adl.h).
+// Define the three it uses unless a CL header already did.
+#if !defined(__OPENCL_CL_PLATFORM_H) && !defined(CLEW_HPP_INCLUDED) && !defined(ADL_SHIM_NO_CL_TYPES)
+typedef float cl_float;
+typedef int cl_int;
+typedef unsigned int cl_uint;
+union alignas(16) cl_float4 {
+    cl_float s[4];
+    struct { cl_float x, y, z, w; };
+};
+typedef cl_float4 cl_float3;  // a 3-vector occupies a 4-vector, as in OpenCL
+#endif
 
 namespace adl {
 
 typedef unsigned long long adlu64;
+
+// status codes and the assertion macro that ADL-side helpers (e.g. the reference's test/Array.h) spell out
+// (names and values as Adl/AdlError.h:24-41; the release-mode macro evaluates and ignores, Adl/AdlError.h:51)
+enum TahoeErrorCodes {
+    TH_NO_ERROR = 0, TH_SUCCESS = 0, TH_FAILURE = 1, TH_ERROR_MEMORY = 2, TH_ERROR_IO = 3, TH_ERROR_PARAMETER = 4,
+    TH_ERROR_INTERNAL = 5, TH_NOT_SUPPORTED = 11, TH_ERROR_NULLPTR = 14,
+};
+#ifndef ADLASSERT
+#define ADLASSERT(x, code) do { if (x) {} } while (0)
+#endif
+#define ADL_SUCCESS 0
+#define ADL_FAILURE 1
 
 enum DeviceType { TYPE_CL = 0, TYPE_DX11 = 1, TYPE_HOST = 2, TYPE_METAL = 3, TYPE_VULKAN = 4, TYPE_CUDA = 5 };
 

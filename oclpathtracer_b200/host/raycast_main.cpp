@@ -15,7 +15,6 @@ using namespace adl;
 
 typedef ptb_triangle Triangle;  // RaytraceTest.cpp:61-76
 typedef ptb_material Material;  // RaytraceTest.cpp:50-59
-typedef ptb_float4 cl_float4;
 
 int main(int argc, char** argv) {
     const char* scene = argc > 1 ? argv[1] : "../test/cornellbox.bin";  // :90

@@ -672,3 +672,84 @@ def test_against_the_genuine_reference_output(dev, pt, cornell, scene):
     assert rr <= 1.5e-3, rr
     assert (d.max(2) == 0).mean() >= 0.97
     assert (d.max(2) > 2).sum() <= 60
+
+
+def test_unmodified_reference_test_program_on_libptb200(dev, pt, cornell, scene, tmp_path):
+    """oracle/_ref/adlTest64_ptb200 = the reference's own test/RaytraceTest.cpp + test/main.cpp, compiled UNMODIFIED with
+    oclpathtracer_b200/host first on the include path (make -C oracle ref; needs /root/reference, so the binary is
+    prebuilt and travels).  Its DeviceTest.RayCast (10000 launches + waitForCompletion, then its own PPM writer) must
+    (1) pass, (2) write exactly the image the batched C-ABI render gives, (3) agree with the image the same program
+    wrote through the reference's OpenCL backend on this GPU (tests/golden/reference_raycast_b200_opencl.npz)."""
+    import glob
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "adlTest64_ptb200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/adlTest64_ptb200 not built (make -C oracle ref needs the reference tree)")
+    env = dict(os.environ, PTB_REF_WORKDIR=str(tmp_path / "ref"))
+    r = subprocess.run([exe, "--gtest_filter=DeviceTest.*"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "[  PASSED  ] 6 tests" in r.stdout and "FAILED" not in r.stdout, r.stdout[-1500:]  # all its DeviceTest cases
+    ppm = glob.glob(str(tmp_path / "ref" / "build" / "rayCastAo_*.ppm"))
+    assert len(ppm) == 1, ppm
+    t = open(ppm[0]).read().split()
+    assert t[:4] == ["P3", "512", "512", "255"]
+    got = np.array(t[4:], np.int32).reshape(512, 512, 3)
+    frame = dev.buffer(512 * 512 * 16)
+    dev.render(scene, pt.default_params(width=512, height=512, first_frame=0, n_frames=10000, mode=pt.MODE_PATH,
+                                        accum=pt.ACCUM_REFERENCE, max_depth=16), frame)
+    ours = pt.to_rgb8(frame.read(np.float32).reshape(-1, 4)).reshape(512, 512, 3).astype(np.int32)
+    frame.close()
+    assert np.array_equal(got, ours)
+    g = np.load(os.path.join(GOLDEN, "reference_raycast_b200_opencl.npz"))["rgb"].astype(np.int32)
+    rr = float(np.sqrt(((got - g) ** 2).mean()) / np.sqrt((g.astype(np.float64) ** 2).mean()))
+    assert rr <= 1.5e-3, rr
+
+
+def test_launch1d_frame_ahead_batching(dev, pt, ob, cornell):
+    """ptb_launch1d traces the next frames of a consecutive-frame loop together (frame-ahead batching) and folds one
+    frame per launch.  The framebuffer after EVERY launch must equal the one-launch-per-frame path bit for bit, also
+    across a scene rewrite in mid-sequence, a jump in the frame index, a repeated frame, a caller-side clear of the
+    framebuffer and a change of BOUNCES."""
+    tris, mats = cornell
+    w, h = 96, 64
+    tb = dev.buffer(36 * 64); mb = dev.buffer(18 * 64)
+    tb.write(tris); mb.write(mats)
+    k = dev.kernel("GenerateColors", "GenerateColors")
+    t2 = tris.copy()
+    for key in ("p1", "p2", "p3"):
+        t2[key][10:12, 1] -= 0.75
+    # (frame index, action before the launch)
+    script = [(f, None) for f in range(0, 23)] + [(23, "rewrite")] + [(f, None) for f in range(24, 40)] + \
+             [(100, None), (101, None), (102, None), (102, None), (103, "clear"), (104, None), (105, "bounces"),
+              (106, None), (107, None), (3, None), (4, None), (5, None)]
+
+    def run(frame_ahead):
+        dev.kernel_set_int(k, "FRAME_AHEAD", frame_ahead)
+        dev.kernel_set_int(k, "BOUNCES", 16)
+        tb.write(tris)
+        fb = dev.buffer(w * h * 16)
+        states = []
+        for frame, action in script:
+            if action == "rewrite":
+                tb.write(t2)
+            elif action == "clear":
+                fb.clear()
+            elif action == "bounces":
+                dev.kernel_set_int(k, "BOUNCES", 5)
+            dev.launch1d(k, [tb, mb, fb], pt.Int4(w, h, frame, 0), w * h)
+            dev.sync()
+            states.append(bits(fb.read(np.float32)).copy())
+        fb.close()
+        return states
+
+    plain = run(0)
+    ahead = run(1)
+    for i, (a, b) in enumerate(zip(plain, ahead)):
+        assert np.array_equal(a, b), f"launch {i} (frame {script[i][0]}) differs"
+    # and the plain path is the oracle's, through the first scene rewrite
+    want, _, _ = ob.render(ob.default_params(w, h, first_frame=0, n_frames=23, mode=3, accum=ob.ACCUM_REFERENCE), tris, mats)
+    assert np.array_equal(plain[22], bits(want).reshape(-1))
+    dev.kernel_set_int(k, "FRAME_AHEAD", 1)
+    dev.kernel_set_int(k, "BOUNCES", 16)
+    tb.close(); mb.close()

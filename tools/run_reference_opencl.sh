@@ -34,3 +34,12 @@ try:
 except Exception as e:
     print("compare failed:", e)
 PY
+# the same unmodified test sources compiled against the ADL-shaped shim (oracle/_ref/adlTest64_ptb200 -> libptb200.so)
+if [ -x oracle/_ref/adlTest64_ptb200 ]; then
+  export PTB_REF_WORKDIR=/tmp/ptb_ref_run_ptb
+  rm -rf $PTB_REF_WORKDIR
+  timeout 300 oracle/_ref/adlTest64_ptb200 --gtest_filter='DeviceTest.*' > "$OUT/reference_test_on_ptb200.log" 2>&1
+  echo "unmodified test on libptb200 rc=$?"; tail -6 "$OUT/reference_test_on_ptb200.log"
+  cp $PTB_REF_WORKDIR/build/*.ppm "$OUT/reference_test_on_ptb200.ppm" 2>/dev/null
+  cmp "$OUT/reference_test_on_ptb200.ppm" "$OUT/ours.ppm" && echo "PPM identical to host/ptb_raycast"
+fi
