@@ -312,7 +312,7 @@ PTD_FI V3 sample_direct(const Ctx& c, const RenderArgs& a, Ray r, uint32_t& seed
 // ---- megakernel: one thread per sample ---------------------------------------------------------
 
 template <int MODE, bool BVH, bool SMALL, bool STATS>
-__global__ void __launch_bounds__(128) k_mega(const SceneDev sc, const RenderArgs a) {
+__global__ void __launch_bounds__(128, (MODE == PTB_MODE_AO && BVH && SMALL) ? 8 : 0) k_mega(const SceneDev sc, const RenderArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Ctx c = stage_scene<BVH, SMALL>(sc, smem);
     uint2 lstack_mem[PTD_LSTACK_ENTRIES];
