@@ -233,8 +233,9 @@ PTD_FI V3 sample_ao(const Ctx& c, Ray r, uint32_t& seed, int ns, float max_dist,
     hit_point_normal(e1, e2, r.o, r.d, h, p, n);
     n = dot(n, r.d) < 0.0f ? n : mul(n, -1.0f);
     uint32_t open = 0;
+    const Frame fr = make_frame(n);  // one tangent frame for all AO rays of the pixel
     for (int k = 0; k < ns; ++k) {
-        const V3 wi = sample_hemisphere_cosine(n, seed);
+        const V3 wi = sample_hemisphere_cosine(n, fr, seed);
         const Ray s = get_ray(add(p, mul(wi, 0.01f)), wi);
         Hit b;
         const uint32_t v0 = qs.visits;

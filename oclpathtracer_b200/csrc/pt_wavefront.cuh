@@ -455,8 +455,9 @@ __global__ void __launch_bounds__(128) wf_shade_first(const SceneDev sc, const R
         nrm = dot(nrm, d) < 0.0f ? nrm : mul(nrm, -1.0f);
         a.samples[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // pending (w = 0)
         w.slot_p[slot] = make_float4(p.x, p.y, p.z, 0.0f);
+        const Frame fr = make_frame(nrm);
         for (int k = 0; k < ns; ++k) {
-            const V3 wi = sample_hemisphere_cosine(nrm, seed);
+            const V3 wi = sample_hemisphere_cosine(nrm, fr, seed);
             w.sq_w[(size_t)k * P + slot] = make_float4(wi.x, wi.y, wi.z, a.ao_max_dist);
         }
         return;
