@@ -382,7 +382,8 @@ def main():
                "synchronous_value": e2e_rays / t_sync / 1e6, "synchronous_ms_per_step": t_sync / args.steps * 1e3,
                "host_checksum": checksum,
                "timing": "host wall clock over K x {ptb_render_host_async (H2D records, render, D2H float4 frame into pinned host memory), "
-                         "ptb_job_wait of the previous step}: D2H of step i overlaps the render of step i+1; synchronous_* waits every step"}
+                         "ptb_job_wait of the previous step}: D2H of step i overlaps the render of step i+1; synchronous_* waits every step. "
+                         "Unlike the device-timed steps there is no L2 flush and no accumulate pass between e2e steps, so this can exceed `value`"}
         for pa in (tp, mp, *outs):
             pa.free()
         dev2.close()

@@ -535,9 +535,21 @@ static ptd::SceneDev scene_dev(const ptb_scene* s) {
 
 // ---- launch helpers -----------------------------------------------------------------------------------
 
+// Opts the kernel into `smem` dynamic bytes and asks for a shared-memory carve-out large enough for every CTA the
+// register file admits: left to itself the driver picked a carve-out that capped the 2M-triangle path kernel at 7 of
+// its 9 register-limited CTAs per SM (ncu: launch__occupancy_limit_shared_mem 7, 43 % warps active).  Returns that
+// CTA count in *per_sm.
 template <class K>
-static int set_smem(K kernel, size_t smem) {
+static int set_smem(K kernel, size_t smem, int block, int* per_sm = nullptr) {
     if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int n = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, block, smem));
+    if (n < 1) n = 1;
+    const size_t want = size_t(n) * (smem + 1024);  // + the 1 KB the system reserves per CTA
+    int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    if (per_sm) *per_sm = n;
     return PTB_OK;
 }
 
@@ -547,10 +559,8 @@ static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::Re
     if (MODE == PTB_MODE_PATH && a.tune[5] == 0) {  // persistent grid with path regeneration (tune[5]=1: one sample per thread)
         const size_t smem = ptd::scene_smem_bytes(sc, BVH, SMALL, block);
         auto k = ptd::k_mega_path_regen<BVH, SMALL, STATS>;
-        if (int rc = set_smem(k, smem)) return rc;
         int per_sm = 0;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, block, smem));
-        if (per_sm < 1) per_sm = 1;
+        if (int rc = set_smem(k, smem, block, &per_sm)) return rc;
         const long long total = (long long)a.frames_in_batch * a.n_local;
         long long grid = (long long)per_sm * dev->prop.multiProcessorCount;
         const long long need = (total + block - 1) / block;
@@ -565,7 +575,7 @@ static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::Re
     const unsigned grid = (unsigned)((total + block - 1) / block);
     const size_t smem = ptd::scene_smem_bytes(sc, BVH, SMALL, block);
     auto k = ptd::k_mega<MODE, BVH, SMALL, STATS>;
-    if (int rc = set_smem(k, smem)) return rc;
+    if (int rc = set_smem(k, smem, block)) return rc;
     k<<<grid, block, smem, dev->stream>>>(sc, a);
     CU_TRY(cudaGetLastError());
     return PTB_OK;
@@ -1218,7 +1228,7 @@ extern "C" int ptb_trace(ptb_device* dev, ptb_scene* scene, int accel, int any_h
 #define PTB_TRACE_CASE(B, A, S)                                                \
     if (bvh == B && any == A && small == S) {                                  \
         auto k = ptd::k_trace<B, A, S>;                                        \
-        if ((rc = set_smem(k, smem))) return rc;                               \
+        if ((rc = set_smem(k, smem, block))) return rc;                               \
         k<<<grid, block, smem, st>>>(sc, a);                                   \
     }
     PTB_TRACE_CASE(true, true, true) PTB_TRACE_CASE(true, true, false) PTB_TRACE_CASE(true, false, true) PTB_TRACE_CASE(true, false, false)
