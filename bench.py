@@ -64,6 +64,20 @@ def dist_env():
     return rank, world, local
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Pins this rank (and so its page-locked host buffers) to the CPUs next to its GPU.  torchrun does not bind
+    ranks; with 8 ranks reading 16 MiB frames back every 0.6 ms, buffers on the far socket cap the aggregate
+    end-to-end rate.  Returns a short description for config.cpu_affinity."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return "numa-local (nvmlDeviceSetCpuAffinity), %d cpus" % len(os.sched_getaffinity(0))
+    except Exception as e:  # plumbing only: never fatal
+        return "unbound (%s)" % type(e).__name__
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -245,6 +259,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the host baseline)")
     torch.cuda.set_device(local)
+    affinity = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = WORKLOADS[args.workload]
@@ -471,7 +486,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "scene_triangles": int(len(tris)),
                        "rays_per_step_per_gpu": int(n_rays_1), "step": "one frame (1 spp) of the full image per rank; rank r renders frame step*N+r",
-                       "integrator": args.integrator, "accel": args.accel, "l2": "256 MiB flush between timed steps",
+                       "integrator": args.integrator, "accel": args.accel, "l2": "256 MiB flush between timed steps", "cpu_affinity": affinity,
                        "parallelism": f"frames dealt round-robin over {world} GPU(s); one NCCL reduce of the accumulators at the end"},
             "spp_per_s": args.steps * world / (ms_total_max * 1e-3), "msamples_per_s": samples_all / (ms_total_max * 1e-3) / 1e6,
             "exchange_ms": ms_exchange, "bvh_build_s": build_s, "sm_count": sm_count,
