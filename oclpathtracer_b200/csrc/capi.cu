@@ -1057,8 +1057,12 @@ extern "C" int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* b
         const int ramp = k->streak >= 5 ? want : (1 << k->streak);  // 2, 4, 8, 16 ... so a short sequence wastes little
         if (want > ramp) want = ramp;
         if (want > 0x7fffffff - z) want = 0x7fffffff - z;
+        k->ahead_count = 0;  // the old batch is gone whatever happens next
+        if (want >= 2 && ensure(&k->ahead, &k->ahead_bytes, size_t(want) * size_t(n_threads) * 16) != PTB_OK) {
+            cudaGetLastError();  // no memory for a batch: fall back to one frame per launch
+            want = 0;
+        }
         if (want >= 2) {
-            if (int rc = ensure(&k->ahead, &k->ahead_bytes, size_t(want) * size_t(n_threads) * 16)) return rc;
             ptb_render_params pb = p;
             pb.n_frames = want;
             if (int rc = render_impl(dev, k->scene, &pb, nullptr, 0, nullptr, 0, nullptr, static_cast<float4*>(k->ahead), PHASE_TRACE)) {

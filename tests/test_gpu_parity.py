@@ -753,3 +753,45 @@ def test_launch1d_frame_ahead_batching(dev, pt, ob, cornell):
     dev.kernel_set_int(k, "FRAME_AHEAD", 1)
     dev.kernel_set_int(k, "BOUNCES", 16)
     tb.close(); mb.close()
+
+
+@pytest.mark.parametrize("integrator", ["mega", "wavefront"])
+def test_ragged_and_degenerate_shapes(dev, pt, ob, cornell, cornell_bvh, scene, integrator):
+    """Edge shapes: a single pixel, sizes below one warp / not a multiple of the CTA, a shard that owns a ragged tail,
+    one AO ray, depth 1, a batch size that does not divide the frame count, frame indices near INT_MAX (the seed is
+    gid + 1103515245*frame + 12345 in uint32 arithmetic, GenerateColors.cl:305-308).  All bit-exact vs the oracle."""
+    tris, mats = cornell
+    _, bvh, _ = cornell_bvh
+    integ = pt.INTEGRATOR_MEGAKERNEL if integrator == "mega" else pt.INTEGRATOR_WAVEFRONT
+    cases = [
+        dict(w=1, h=1, mode=3, n_frames=5, fpb=2, first=0, max_depth=16),
+        dict(w=7, h=3, mode=1, n_frames=3, fpb=2, first=0, ao_samples=1),
+        dict(w=33, h=17, mode=2, n_frames=4, fpb=3, first=2147483000),
+        dict(w=130, h=1, mode=3, n_frames=3, fpb=0, first=7, max_depth=1),
+        dict(w=61, h=29, mode=3, n_frames=3, fpb=2, first=0, max_depth=4, shard=(2, 3, 50)),
+        dict(w=40, h=40, mode=0, n_frames=1, fpb=1, first=0, shard=(6, 7, 64)),
+    ]
+    for cs in cases:
+        kw = dict(n_frames=cs["n_frames"], first_frame=cs["first"], mode=cs["mode"], max_depth=cs.get("max_depth", 8),
+                  ao_samples=cs.get("ao_samples", 16))
+        if "shard" in cs:
+            kw.update(shard_index=cs["shard"][0], shard_count=cs["shard"][1], shard_block=cs["shard"][2])
+        for accum in (pt.ACCUM_LINEAR, pt.ACCUM_REFERENCE):
+            prm = pt.default_params(width=cs["w"], height=cs["h"], accum=accum, frames_per_batch=cs["fpb"],
+                                    integrator=integ, collect_stats=1, **kw)
+            n_local = pt.local_pixels(prm)
+            frame = dev.buffer(max(n_local, 1) * 16)
+            stats = dev.buffer(max(n_local, 1) * 32)
+            frame.clear()
+            ctr = dev.render(scene, prm, frame, stats, want_counters=True)
+            fb = frame.read(np.float32).reshape(-1, 4)[:n_local]
+            st = stats.read(pt.STATS_DTYPE)[:n_local]
+            frame.close(); stats.close()
+            oprm = oracle_params(ob, tris, cs["w"], cs["h"], accum=accum, use_bvh=1, **kw)
+            ofb, ost, octr = ob.render(oprm, tris, mats, bvh=bvh, want_stats=True)
+            assert len(ofb) == n_local, cs
+            np.testing.assert_array_equal(bits(fb), bits(ofb), err_msg=str(cs))
+            for f in ost.dtype.names:
+                np.testing.assert_array_equal(st[f], ost[f], err_msg=f"{f} {cs}")
+            for k in ("rays_closest", "rays_any", "nodes", "tri_tests"):
+                assert ctr[k] == octr[k], (k, cs)
