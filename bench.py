@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--fpb", type=int, default=0, help="frames_per_batch override")
     ap.add_argument("--smem-nodes", type=int, default=0, help="BVH nodes staged in shared memory (0 = default)")
     ap.add_argument("--max-leaf", type=int, default=0, help="BVH max triangles per leaf (0 = default)")
+    ap.add_argument("--sah-traverse", type=float, default=0.0, help="SAH node-visit cost (0 = default 1.2)")
     ap.add_argument("--gpu-build", action="store_true", help="build the BVH on the device (LBVH) instead of the host SAH builder")
     ap.add_argument("--ab", action="store_true", help="also time the other integrator and brute force (extra keys)")
     return ap.parse_args()
@@ -274,8 +275,10 @@ def main():
     tris, mats, light = load_scene(pt, wl)
     t0 = time.perf_counter()
     bp = None
-    if args.smem_nodes or args.max_leaf:
+    if args.smem_nodes or args.max_leaf or args.sah_traverse:
         bp = pt.bvh_params()
+        if args.sah_traverse:
+            bp.traverse_cost = args.sah_traverse
         if args.smem_nodes:
             bp.smem_nodes = args.smem_nodes
         if args.max_leaf:

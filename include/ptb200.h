@@ -128,7 +128,8 @@ typedef struct ptb_bvh_params {
     float pad_rel;      /* child boxes are grown by pad_rel * scene diagonal, default 1e-4 */
     int32_t n_bins;     /* SAH bins, default 16 */
     int32_t smem_nodes; /* top-of-tree nodes laid out first (BFS) for shared-memory staging, default 1024 */
-    int32_t reserved[4];
+    float traverse_cost; /* SAH cost of one node visit relative to one triangle test (<= 0: default 1.2) */
+    int32_t reserved[3];
 } ptb_bvh_params;
 void ptb_bvh_params_default(ptb_bvh_params* p);
 

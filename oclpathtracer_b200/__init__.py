@@ -71,7 +71,7 @@ class Counters(C.Structure):
 
 class BvhParams(C.Structure):
     _fields_ = [("max_leaf", C.c_int32), ("pad_rel", C.c_float), ("n_bins", C.c_int32), ("smem_nodes", C.c_int32),
-                ("reserved", C.c_int32 * 4)]
+                ("traverse_cost", C.c_float), ("reserved", C.c_int32 * 3)]
 
 
 class Int4(C.Structure):

@@ -57,7 +57,8 @@ struct Builder {
     std::vector<TmpNode> nodes;
     std::vector<int32_t> order;  // leaf order -> caller index
     int max_leaf, n_bins;
-    static constexpr double kTraverse = 1.2, kIntersect = 1.0;
+    static constexpr double kIntersect = 1.0;
+    double kTraverse = 1.2;  // ptb_bvh_params.traverse_cost
 
     // returns child reference; fills the exact bounds of [b, e)
     int32_t build(int b, int e, bool force_split, Box* bounds) {
@@ -178,6 +179,7 @@ int build_bvh(const ptb_triangle* tris, int n_tris, const ptb_bvh_params& params
     Builder B;
     B.max_leaf = std::min(std::max(params.max_leaf, 1), PTB_BVH_MAX_LEAF);
     B.n_bins = std::min(std::max(params.n_bins, 2), 256);
+    if (params.traverse_cost > 0.0f) B.kTraverse = params.traverse_cost;
     B.prims.resize(size_t(n_tris));
     Box scene; scene.reset();
     for (int i = 0; i < n_tris; ++i) {
@@ -397,4 +399,5 @@ extern "C" void ptb_bvh_params_default(ptb_bvh_params* p) {
     p->pad_rel = 1e-4f;
     p->n_bins = 16;
     p->smem_nodes = 1024;
+    p->traverse_cost = 1.2f;
 }
