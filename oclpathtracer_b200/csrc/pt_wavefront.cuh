@@ -141,7 +141,7 @@ PTD_FI void trace_persistent(const Ctx& c, IO& io, const unsigned int n_rays, un
                 idx = base + (unsigned int)__popc(idle & ((1u << lane) - 1u));
                 float tmax;
                 if (idx < n_rays && io.load(idx, o, d, tmax)) {
-                    invd = mk(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+                    invd = safe_rcp3(d);
                     ood = mk(o.x * invd.x, o.y * invd.y, o.z * invd.z);
                     best_t = tmax; best_u = best_v = 0.f; best_pos = best_idx = -1;
                     cur = 0; sp = 0;
