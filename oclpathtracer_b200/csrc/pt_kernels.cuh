@@ -86,9 +86,10 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
     c.g_mats = sc.mats;
     c.stride_bytes = blockDim.x * 4u;
     const uint32_t stack_bytes = (NODES && !sc.lstack) ? (uint32_t)sc.stack_depth * blockDim.x * 4u : 0u;
-    c.s_stack_ref = smem_u32(s_stack) + threadIdx.x * 4u;
-    c.s_stack_tn = c.s_stack_ref + stack_bytes;
-    c.s_scratch = c.s_stack_tn + stack_bytes;
+    // two disjoint areas: warps of one CTA can be in a closest-hit and an any-hit query at the same time (AO, DIRECT)
+    c.s_stack64 = smem_u32(s_stack) + threadIdx.x * 8u;                       // (ref, entry distance) pairs
+    c.s_stack_ref = smem_u32(s_stack) + 2u * stack_bytes + threadIdx.x * 4u;  // any-hit: references only
+    c.s_scratch = smem_u32(s_stack) + 3u * stack_bytes + threadIdx.x * 4u;
     c.smem_nodes = sc.smem_nodes;
     c.n_tris = sc.n_tris;
     c.lstack = nullptr;
@@ -100,7 +101,7 @@ static inline size_t scene_smem_bytes(const SceneDev& sc, bool bvh, bool small, 
     size_t b = 16;
     if (bvh) b += (size_t)sc.smem_nodes * (small ? 128 : 64);
     if (small) b += (size_t)sc.n_tris * 48 + (size_t)sc.n_mats * 32;
-    if (bvh && !sc.lstack) b += (size_t)sc.stack_depth * block * 8;
+    if (bvh && !sc.lstack) b += (size_t)sc.stack_depth * block * 12;  // closest-hit pairs (8 B) + any-hit references (4 B)
     return b + scratch_per_thread * block;
 }
 
@@ -313,7 +314,7 @@ PTD_FI V3 sample_direct(const Ctx& c, const RenderArgs& a, Ray r, uint32_t& seed
 // ---- megakernel: one thread per sample ---------------------------------------------------------
 
 template <int MODE, bool BVH, bool SMALL, bool STATS>
-__global__ void __launch_bounds__(128, (MODE == PTB_MODE_AO && BVH && SMALL) ? 8 : 0) k_mega(const SceneDev sc, const RenderArgs a) {
+__global__ void __launch_bounds__(128, ((MODE == PTB_MODE_AO || MODE == PTB_MODE_DIRECT) && BVH && SMALL) ? 8 : 0) k_mega(const SceneDev sc, const RenderArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Ctx c = stage_scene<BVH, SMALL>(sc, smem);
     uint2 lstack_mem[PTD_LSTACK_ENTRIES];
