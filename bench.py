@@ -122,6 +122,10 @@ class ClockSampler:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
+        for _ in range(20):  # a run shorter than nvidia-smi's start-up: take its first rows (just after the timed region)
+            if self.rows:
+                break
+            time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
