@@ -201,7 +201,11 @@ int ptb_host_free(void* p);
  * and returns the totals since the previous read.  kernel_launches counts this
  * library's own kernel launches (always on).                                      */
 int ptb_device_profile(ptb_device* dev, int enable);
-/* experiment knobs for A/B measurements, index 0..7 (results never change) */
+/* experiment knobs for A/B measurements (results never change).  index: 1 = log2 multiplier of
+ * the frame-ahead batch of ptb_launch1d; 2 = 2: keep the traversal stack of large scenes in shared memory; 3 = CTA
+ * size 64 | 32 (default 128); 4 = BVH nodes staged per CTA for large scenes (default 64); 5 = 1: one sample per
+ * thread instead of path regeneration; 6 = 1: wavefront stages without persistent ray fetch; 7 = idle-lane count
+ * that triggers a refill (default 8); 0 = unused.                                                                  */
 int ptb_device_set_tuning(ptb_device* dev, int index, int value);
 int ptb_device_profile_read(ptb_device* dev, float* integrator_ms, float* resolve_ms, int* integrator_launches,
                             uint64_t* kernel_launches);

@@ -765,7 +765,7 @@ extern "C" int ptb_render(ptb_device* dev, ptb_scene* scene, const ptb_render_pa
 
 // content hash of the caller's records (decides whether the resident scene must be rebuilt).  Four independent
 // multiply-xorshift lanes over 32-byte stripes: the 2M-triangle scene is 128 MB and is hashed on every call.
-static uint64_t fnv1a(const void* p, size_t n, uint64_t h) {
+static uint64_t content_hash(const void* p, size_t n, uint64_t h) {
     const unsigned char* b = static_cast<const unsigned char*>(p);
     uint64_t l0 = h ^ 0x9E3779B97F4A7C15ull, l1 = h ^ 0xC2B2AE3D27D4EB4Full, l2 = h ^ 0x165667B19E3779F9ull, l3 = h ^ 0x27D4EB2F165667C5ull;
     size_t i = 0;
@@ -860,8 +860,8 @@ extern "C" int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, 
         (rc = ensure_buffer(dev, &sl.frame, fb)) || (sb && (rc = ensure_buffer(dev, &sl.stats, sb))))
         return rc;
     // 2. resident scene (BVH + relaid records) is rebuilt only when the records changed
-    uint64_t h = fnv1a(tris, tb, 1469598103934665603ull);
-    h = fnv1a(mats, mb, h);
+    uint64_t h = content_hash(tris, tb, 1469598103934665603ull);
+    h = content_hash(mats, mb, h);
     const bool scene_changed = !dev->host_scene || dev->host_scene_hash != h;
     const void* src_t = tris;
     const void* src_m = mats;
@@ -1017,8 +1017,8 @@ extern "C" int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* b
         std::vector<ptb_material> hm(nm);
         CU_TRY(cudaMemcpyAsync(hm.data(), mb->d_ptr, size_t(nm) * sizeof(ptb_material), cudaMemcpyDeviceToHost, dev->stream));
         CU_TRY(cudaStreamSynchronize(dev->stream));
-        uint64_t h = fnv1a(ht.data(), ht.size() * sizeof(ptb_triangle), 1469598103934665603ull);
-        h = fnv1a(hm.data(), hm.size() * sizeof(ptb_material), h);
+        uint64_t h = content_hash(ht.data(), ht.size() * sizeof(ptb_triangle), 1469598103934665603ull);
+        h = content_hash(hm.data(), hm.size() * sizeof(ptb_material), h);
         if (!k->scene || h != k->hash) {
             if (k->scene) ptb_scene_destroy(k->scene);
             k->scene = nullptr;
