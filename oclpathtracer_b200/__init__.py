@@ -313,6 +313,12 @@ class Device:
     def stream(self):
         return lib().ptb_device_stream(self._h)
 
+    def memory(self):
+        """(free, total) bytes of device memory."""
+        f, t = C.c_size_t(), C.c_size_t()
+        _check(lib().ptb_device_memory(self._h, C.byref(f), C.byref(t)))
+        return f.value, t.value
+
     def set_tuning(self, index, value):
         _check(lib().ptb_device_set_tuning(self._h, index, value))
 

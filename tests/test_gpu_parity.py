@@ -795,3 +795,34 @@ def test_ragged_and_degenerate_shapes(dev, pt, ob, cornell, cornell_bvh, scene, 
                 np.testing.assert_array_equal(st[f], ost[f], err_msg=f"{f} {cs}")
             for k in ("rays_closest", "rays_any", "nodes", "tri_tests"):
                 assert ctr[k] == octr[k], (k, cs)
+
+
+def test_no_device_memory_leak(pt, cornell):
+    """Devices, scenes, buffers, the host pipeline and the frame-ahead batch release what they allocate."""
+    tris, mats = cornell
+    probe = pt.Device(0)
+    free0 = None
+    for it in range(6):
+        d = pt.Device(0)
+        sc = d.scene(tris, mats)
+        fb = d.buffer(256 * 256 * 16)
+        d.render(sc, pt.default_params(width=256, height=256, n_frames=3, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR), fb)
+        d.render(sc, pt.default_params(width=256, height=256, n_frames=2, mode=pt.MODE_AO, accum=pt.ACCUM_LINEAR,
+                                       integrator=pt.INTEGRATOR_WAVEFRONT), fb)
+        d.render_host(tris, mats, pt.default_params(width=128, height=128, n_frames=1, mode=pt.MODE_DIRECT))
+        tb = d.buffer(tris.nbytes); mb = d.buffer(mats.nbytes)
+        tb.write(tris); mb.write(mats)
+        k = d.kernel("GenerateColors", "GenerateColors")
+        for f in range(12):  # long enough to allocate a frame-ahead batch
+            d.launch1d(k, [tb, mb, fb], pt.Int4(256, 256, f, 0), 256 * 256)
+        d.sync()
+        for b in (tb, mb, fb):
+            b.close()
+        sc.close()
+        d.close()
+        free, _ = probe.memory()
+        if it == 1:
+            free0 = free  # after the first full cycle (context-level pools are warm)
+        elif it > 1:
+            assert free >= free0 - (8 << 20), (it, free0, free)
+    probe.close()
