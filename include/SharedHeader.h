@@ -94,7 +94,8 @@ typedef struct ptb_bvh_node4 {
     int32_t pad3;
 } ptb_bvh_node4;
 
-#define PTB_BVH_WIDTH 4 /* slots of a ptb_bvh_node4 */
+#define PTB_BVH_WIDTH 4
+#define PTB_MAX_PEERS 7 /* peer images a gathering render can store into (8 GPUs per node) */ /* slots of a ptb_bvh_node4 */
 #define PTB_BVH_EMPTY 0x7fffffff
 #define PTB_BVH_LEAF_REF(first, count) (~(int32_t)(((uint32_t)(first) << 3) | (uint32_t)((count)-1)))
 #define PTB_BVH_LEAF_FIRST(ref) ((int32_t)((uint32_t)(~(ref)) >> 3))

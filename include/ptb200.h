@@ -178,6 +178,17 @@ int ptb_render(ptb_device* dev, ptb_scene* scene, const ptb_render_params* param
 /* End-to-end convenience with HOST buffers: uploads the scene records (H2D),
  * (re)builds the resident scene if the records changed, renders, reads the frame
  * (and stats) back (D2H) and synchronises.  out_rgba: float4 per local pixel. */
+/* Image sharding with the exchange fused into the render (BUILD-DEFINED; the reference is single-device).  Every
+ * rank owns a FULL image; ptb_buffer_ipc_export / _import map the images of the other ranks' processes (CUDA IPC:
+ * peer memory over NVLink / NVSwitch).  ptb_render_gather renders this rank's shard (params->shard_*) and stores
+ * each finished pixel at its global position in full_frame and in every peer image, so no collective and no
+ * un-interleave pass follows -- only a barrier before the images are read.  With accum = REFERENCE the running state
+ * is read from full_frame.  Results are bit-identical to a single-device ptb_render of the whole image.          */
+int ptb_buffer_ipc_export(ptb_buffer* buf, void* handle64 /* 64 bytes out */);
+int ptb_buffer_ipc_import(ptb_device* dev, const void* handle64, size_t bytes, ptb_buffer** out);
+int ptb_render_gather(ptb_device* dev, ptb_scene* scene, const ptb_render_params* params, ptb_buffer* full_frame,
+                      ptb_buffer* const* peer_frames, int n_peers /* 0..PTB_MAX_PEERS */, ptb_counters* counters);
+
 int ptb_render_host(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats, int n_mats,
                     const ptb_render_params* params, float* out_rgba, ptb_pixel_stats* out_stats,
                     ptb_counters* counters);

@@ -94,6 +94,7 @@ EXPORTS = [
     "ptb_light_from_quad", "ptb_free", "ptb_to_rgb8", "ptb_write_ppm", "ptb_bvh_params_default",
     "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_create_gpu", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_bvh_width", "ptb_scene_copy_bvh",
     "ptb_render_params_default", "ptb_render_local_pixels", "ptb_render", "ptb_render_host",
+    "ptb_buffer_ipc_export", "ptb_buffer_ipc_import", "ptb_render_gather",
     "ptb_render_host_async", "ptb_job_wait", "ptb_host_alloc", "ptb_host_free", "ptb_trace",
     "ptb_device_profile", "ptb_device_profile_read", "ptb_device_set_tuning", "ptb_test_sincos", "ptb_test_pow", "ptb_test_rng", "ptb_test_camera",
 ]
@@ -355,6 +356,17 @@ class Device:
                                 C.byref(ctr) if ctr is not None else None))
         return ctr.as_dict() if ctr is not None else None
 
+    def ipc_import(self, handle, nbytes):
+        return Buffer(self, nbytes, ipc_handle=handle)
+
+    def render_gather(self, scene, params, full_frame, peer_frames=(), want_counters=False):
+        """Render this rank's shard and store every pixel at its global position in full_frame and the peers' images."""
+        ctr = Counters() if want_counters else None
+        arr = (C.c_void_p * max(1, len(peer_frames)))(*[b._h for b in peer_frames])
+        _check(lib().ptb_render_gather(self._h, scene._h, C.byref(params), full_frame._h, arr, len(peer_frames),
+                                       C.byref(ctr) if ctr is not None else None))
+        return ctr.as_dict() if ctr is not None else None
+
     def render_host(self, tris, mats, params, out=None, want_stats=False, want_counters=True):
         n = local_pixels(params)
         if out is None:
@@ -453,11 +465,13 @@ class Device:
 class Buffer:
     """adl::Buffer<T> (Adl/Adl.h:203-265) over ptb_buffer."""
 
-    def __init__(self, dev, nbytes, device_ptr=None):
+    def __init__(self, dev, nbytes, device_ptr=None, ipc_handle=None):
         self.dev = dev
         self.nbytes = nbytes
         self._h = C.c_void_p()
-        if device_ptr is None:
+        if ipc_handle is not None:  # another process's buffer, mapped as peer memory
+            _check(lib().ptb_buffer_ipc_import(dev._h, C.c_char_p(bytes(ipc_handle)), nbytes, C.byref(self._h)))
+        elif device_ptr is None:
             _check(lib().ptb_buffer_create(dev._h, nbytes, C.byref(self._h)))
         else:
             _check(lib().ptb_buffer_wrap(dev._h, C.c_void_p(device_ptr), nbytes, C.byref(self._h)))
@@ -479,6 +493,12 @@ class Buffer:
 
     def clear(self):
         _check(lib().ptb_buffer_clear(self._h))
+
+    def ipc_export(self):
+        """64-byte CUDA IPC handle; another process maps the buffer with Device.ipc_import(handle, nbytes)."""
+        h = C.create_string_buffer(64)
+        _check(lib().ptb_buffer_ipc_export(self._h, h))
+        return h.raw
 
     def device_ptr(self):
         return lib().ptb_buffer_device_ptr(self._h)

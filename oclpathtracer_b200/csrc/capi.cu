@@ -83,6 +83,7 @@ struct ptb_buffer {
     void* d_ptr = nullptr;
     size_t bytes = 0;
     bool owned = true;
+    bool ipc = false;       // mapping of another process's buffer (ptb_buffer_ipc_import)
     void* h_map = nullptr;  // pinned staging for map/unmap
     uint64_t version = 0;
 };
@@ -296,6 +297,10 @@ extern "C" int ptb_buffer_destroy(ptb_buffer* buf) {
     if (buf->owned && buf->d_ptr) {
         cudaStreamSynchronize(buf->dev->stream);
         cudaFree(buf->d_ptr);
+    }
+    if (buf->ipc && buf->d_ptr) {
+        cudaStreamSynchronize(buf->dev->stream);
+        cudaIpcCloseMemHandle(buf->d_ptr);
     }
     buf->dev->live_buffers--;
     delete buf;
@@ -649,14 +654,16 @@ static int validate(const ptb_render_params* p) {
 enum { PHASE_BOTH = 0, PHASE_TRACE = 1, PHASE_RESOLVE = 2 };
 static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_params* p, float4* d_frame, size_t frame_bytes,
                        ptb_pixel_stats* d_stats, size_t stats_bytes, ptb_counters* counters, float4* ext_samples = nullptr,
-                       int phase = PHASE_BOTH) {
+                       int phase = PHASE_BOTH, float4* const* peers = nullptr, int n_peers = -1) {
     if (!dev || !scene || (!d_frame && phase != PHASE_TRACE)) return fail(PTB_E_INVALID, "ptb_render: null argument");
     if (int rc = validate(p)) return rc;
     if (scene->dev != dev) return fail(PTB_E_INVALID, "ptb_render: scene belongs to another device");
     if (set_device(dev)) return PTB_E_CUDA;
     const int n_local = ptb_render_local_pixels(p);
     if (n_local <= 0) return fail(PTB_E_INVALID, "ptb_render: shard owns no pixels");
-    if (phase != PHASE_TRACE && frame_bytes < size_t(n_local) * 16) return fail(PTB_E_INVALID, "ptb_render: frame buffer too small (%zu < %zu)", frame_bytes, size_t(n_local) * 16);
+    const bool gather = n_peers >= 0;  // d_frame (and the peers) are full images indexed by global pixel id
+    const size_t frame_need = gather ? size_t(p->width) * size_t(p->height) * 16 : size_t(n_local) * 16;
+    if (phase != PHASE_TRACE && frame_bytes < frame_need) return fail(PTB_E_INVALID, "ptb_render: frame buffer too small (%zu < %zu)", frame_bytes, frame_need);
     if (d_stats && stats_bytes < size_t(n_local) * sizeof(ptb_pixel_stats)) return fail(PTB_E_INVALID, "ptb_render: stats buffer too small");
     if (p->mode == PTB_MODE_DIRECT && (p->light_quad < 0 || p->light_quad >= scene->n_mats))
         return fail(PTB_E_INVALID, "ptb_render: light_quad %d out of range", p->light_quad);
@@ -739,6 +746,8 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
         r.accum = p->accum; r.first_batch = f0 == 0; r.last_batch = f0 + nb >= p->n_frames;
         r.total_frames = p->n_frames;
         r.sum = static_cast<float4*>(dev->sum); r.frame = d_frame;
+        r.gather = gather ? 1 : 0; r.n_peers = gather ? n_peers : 0; r.shard = a.shard;
+        for (int k = 0; k < PTB_MAX_PEERS; ++k) r.peers[k] = (gather && k < n_peers) ? peers[k] : nullptr;
         ptd::k_resolve<<<(n_local + 255) / 256, 256, 0, dev->stream>>>(r);
         CU_TRY(cudaGetLastError());
         dev->kernel_launches += 1;
@@ -761,6 +770,51 @@ extern "C" int ptb_render(ptb_device* dev, ptb_scene* scene, const ptb_render_pa
     if (!frame) return fail(PTB_E_INVALID, "ptb_render: null frame buffer");
     return render_impl(dev, scene, params, static_cast<float4*>(frame->d_ptr), frame->bytes,
                        stats ? static_cast<ptb_pixel_stats*>(stats->d_ptr) : nullptr, stats ? stats->bytes : 0, counters);
+}
+
+// ---- image-sharded render that delivers straight into the full images of this rank and its peers ----------------
+// Buffers of other processes are mapped with CUDA IPC (NVLink / NVSwitch peer memory); k_resolve stores every finished
+// pixel at its global position in each image, so the exchange step of image sharding needs no collective
+// and no un-interleave pass: only a barrier before the images are read.
+
+extern "C" int ptb_buffer_ipc_export(ptb_buffer* buf, void* handle64) {
+    if (!buf || !handle64) return fail(PTB_E_INVALID, "ptb_buffer_ipc_export: null argument");
+    if (!buf->owned) return fail(PTB_E_INVALID, "ptb_buffer_ipc_export: only buffers created by ptb_buffer_create can be exported");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (set_device(buf->dev)) return PTB_E_CUDA;
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, buf->d_ptr));
+    std::memcpy(handle64, &h, sizeof h);
+    return PTB_OK;
+}
+
+extern "C" int ptb_buffer_ipc_import(ptb_device* dev, const void* handle64, size_t bytes, ptb_buffer** out) {
+    if (!dev || !handle64 || !out) return fail(PTB_E_INVALID, "ptb_buffer_ipc_import: null argument");
+    *out = nullptr;
+    if (set_device(dev)) return PTB_E_CUDA;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof h);
+    void* p = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ptb_buffer* b = new ptb_buffer();
+    b->dev = dev; b->d_ptr = p; b->bytes = bytes; b->owned = false; b->ipc = true;
+    dev->live_buffers++;
+    *out = b;
+    return PTB_OK;
+}
+
+extern "C" int ptb_render_gather(ptb_device* dev, ptb_scene* scene, const ptb_render_params* params, ptb_buffer* full_frame,
+                                 ptb_buffer* const* peer_frames, int n_peers, ptb_counters* counters) {
+    if (!full_frame || n_peers < 0 || n_peers > PTB_MAX_PEERS || (n_peers && !peer_frames))
+        return fail(PTB_E_INVALID, "ptb_render_gather: bad arguments (0..%d peers)", PTB_MAX_PEERS);
+    float4* pp[PTB_MAX_PEERS] = {};
+    const size_t need = params ? size_t(params->width) * size_t(params->height) * 16 : 0;
+    for (int k = 0; k < n_peers; ++k) {
+        if (!peer_frames[k] || peer_frames[k]->bytes < need) return fail(PTB_E_INVALID, "ptb_render_gather: peer image %d is missing or too small", k);
+        pp[k] = static_cast<float4*>(peer_frames[k]->d_ptr);
+    }
+    return render_impl(dev, scene, params, static_cast<float4*>(full_frame->d_ptr), full_frame->bytes, nullptr, 0, counters,
+                       nullptr, PHASE_BOTH, pp, n_peers);
 }
 
 // content hash of the caller's records (decides whether the resident scene must be rebuilt).  Four independent

@@ -449,13 +449,24 @@ struct ResolveArgs {
     int total_frames;
     float4* sum;    // linear running sum (xyz)
     float4* frame;  // output / gamma-space state
+    // gather mode (ptb_render_gather): `frame` and `peers[]` are FULL images indexed by the global pixel id; the resolved
+    // pixel is stored into this rank's image and into every peer's (their memory is mapped over NVLink)
+    int gather, n_peers;
+    Shard shard;
+    float4* peers[PTB_MAX_PEERS];
 };
+
+PTD_FI void resolve_store(const ResolveArgs& a, size_t at, float4 v) {
+    a.frame[at] = v;
+    for (int k = 0; k < a.n_peers; ++k) a.peers[k][at] = v;  // 16-byte remote stores, coalesced per 64-pixel block
+}
 
 __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= a.n_local) return;
+    const size_t at = a.gather ? (size_t)gid_of_local(a.shard, li) : (size_t)li;
     if (a.accum == PTB_ACCUM_REFERENCE) {
-        float4 cur = a.frame[li];
+        float4 cur = a.frame[at];
         V3 state = xyz(cur);
         float w = cur.w;
         for (int fi = 0; fi < a.frames_in_batch; ++fi) {
@@ -470,7 +481,7 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
             }
             w = 1.0f;
         }
-        a.frame[li] = make_float4(state.x, state.y, state.z, w);
+        resolve_store(a, at, make_float4(state.x, state.y, state.z, w));
     } else {
         V3 s = a.first_batch ? mk(0.0f, 0.0f, 0.0f) : xyz(a.sum[li]);
         for (int fi = 0; fi < a.frames_in_batch; ++fi) {
@@ -479,7 +490,7 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
         }
         if (a.last_batch) {
             const float nf = (float)a.total_frames;
-            a.frame[li] = make_float4(s.x / nf, s.y / nf, s.z / nf, 1.0f);
+            resolve_store(a, at, make_float4(s.x / nf, s.y / nf, s.z / nf, 1.0f));
         } else {
             a.sum[li] = make_float4(s.x, s.y, s.z, 0.0f);
         }

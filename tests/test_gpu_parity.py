@@ -826,3 +826,40 @@ def test_no_device_memory_leak(pt, cornell):
         elif it > 1:
             assert free >= free0 - (8 << 20), (it, free0, free)
     probe.close()
+
+
+def test_render_gather_single_process(dev, pt, cornell, scene):
+    """ptb_render_gather without peers: four shards rendered one after the other into ONE full image give exactly the
+    single-device image (pixels land at their global position; REFERENCE accumulation resumes from that image)."""
+    w, h, world, block = 130, 47, 4, 64
+    full = dev.buffer(w * h * 16)
+    ref = dev.buffer(w * h * 16)
+    for accum, chunks in ((pt.ACCUM_LINEAR, [(0, 3)]), (pt.ACCUM_REFERENCE, [(0, 2), (2, 2)])):
+        full.clear(); ref.clear()
+        for first, n in chunks:
+            for r in range(world):
+                dev.render_gather(scene, pt.default_params(width=w, height=h, first_frame=first, n_frames=n, mode=pt.MODE_AO, accum=accum,
+                                                           shard_index=r, shard_count=world, shard_block=block), full)
+            dev.render(scene, pt.default_params(width=w, height=h, first_frame=first, n_frames=n, mode=pt.MODE_AO, accum=accum), ref)
+        np.testing.assert_array_equal(full.read(np.uint32), ref.read(np.uint32))
+    with pytest.raises(pt.PtbError, match="too small"):
+        small = dev.buffer(64)
+        try:
+            dev.render_gather(scene, pt.default_params(width=w, height=h, shard_index=0, shard_count=2), small)
+        finally:
+            small.close()
+    full.close(); ref.close()
+
+
+def test_render_gather_over_ipc(pt):
+    """Two processes (both on cuda:0 here; one per GPU on a multi-GPU box) map each other's full image with CUDA IPC and
+    render their shard with the exchange fused into the resolve kernel; both images equal the single-device render."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ, PTB_TEST_ONE_GPU="1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29631", os.path.join(ROOT, "tests", "_gather_worker.py")],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("identical=True") == 4, r.stdout
