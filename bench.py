@@ -53,6 +53,11 @@ def parse():
     ap.add_argument("--smem-nodes", type=int, default=0, help="BVH nodes staged in shared memory (0 = default)")
     ap.add_argument("--max-leaf", type=int, default=0, help="BVH max triangles per leaf (0 = default)")
     ap.add_argument("--sah-traverse", type=float, default=0.0, help="SAH node-visit cost (0 = default 1.2)")
+    ap.add_argument("--sharding", choices=["frames", "image"], default="frames",
+                    help="frames (default): rank r renders whole frames = r mod N, weak scaling, one NCCL reduce at the end; "
+                         "image: every step is ONE image tile-sharded over the ranks (64-pixel blocks round-robin) with the gather "
+                         "fused into the resolve kernel over peer memory, strong scaling")
+    ap.add_argument("--spp-per-step", type=int, default=1, help="frames rendered per step (image sharding)")
     ap.add_argument("--gpu-build", action="store_true", help="build the BVH on the device (LBVH) instead of the host SAH builder")
     ap.add_argument("--ab", action="store_true", help="also time the other integrator and brute force (extra keys)")
     return ap.parse_args()
@@ -300,8 +305,24 @@ def main():
         return make_params(pt, wl, first_frame=step_frame, integrator=integ, accel=accel, frames_per_batch=args.fpb,
                            light_p1=light[0], light_ea=light[1], light_eb=light[2], **kw)
 
+    image_mode = args.sharding == "image"
+    full = None
+    peers = []
+    if image_mode:
+        # every rank owns the full image; the other ranks' images are mapped as peer memory (CUDA IPC over NVLink)
+        full = dev.buffer(npix * 16)
+        full.clear()
+        dev.sync()
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, full.ipc_export())
+            peers = [dev.ipc_import(handles[r], npix * 16) for r in range(world) if r != rank]
+
     def step(i, profile_ctr=None):
         """one pass of the hot path over one frame, inputs resident in HBM"""
+        if image_mode:  # this rank's tiles of frame(s) i, delivered into every rank's image by the resolve kernel
+            return dev.render_gather(scene, params(i * args.spp_per_step, n_frames=args.spp_per_step, shard_index=rank,
+                                                   shard_count=world, shard_block=64), full, peers, want_counters=profile_ctr)
         ctr = dev.render(scene, params(i * world + rank), frame, None, want_counters=profile_ctr)
         accum_t.add_(frame_t)
         return ctr
@@ -311,7 +332,8 @@ def main():
     for i in range(args.steps):
         c = step(i, profile_ctr=True)
         rays_per_step.append(c["rays_closest"] + c["rays_any"])
-    stat_ctr = dev.render(scene, params(rank, collect_stats=1), frame, None, want_counters=True)
+    stat_ctr = dev.render(scene, params(rank, collect_stats=1, **({"shard_index": rank, "shard_count": world, "shard_block": 64} if image_mode else {})),
+                          frame, None, want_counters=True)
     accum_t.zero_()
 
     sampler = ClockSampler(local)
@@ -334,7 +356,7 @@ def main():
         ev[i][1].record(stream)
     # the job's single exchange: combine the per-rank accumulators (timed, once)
     ev[-1][0].record(stream)
-    if world > 1:
+    if world > 1 and not image_mode:
         dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
     ev[-1][1].record(stream)
     torch.cuda.synchronize()
@@ -355,11 +377,11 @@ def main():
     else:
         ms_total_max, rays_all = ms_total, float(sum(rays_per_step))
     value = rays_all / (ms_total_max * 1e-3) / 1e6
-    samples_all = npix * args.steps * world
+    samples_all = npix * args.steps * (args.spp_per_step if image_mode else world)
 
     # ---- e2e: the same metric through the host-buffer C-ABI call (H2D scene records, D2H frame) ----------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not image_mode:
         dev2 = pt.Device(local)
         # page-locked host buffers: the caller's records (inputs) and two result frames (double buffering)
         tp, mp = pt.PinnedArray(tris.shape, tris.dtype), pt.PinnedArray(mats.shape, mats.dtype)
@@ -490,12 +512,16 @@ def main():
         line = {
             "metric": "Mrays/sec (primary+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if image_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "scene_triangles": int(len(tris)),
-                       "rays_per_step_per_gpu": int(n_rays_1), "step": "one frame (1 spp) of the full image per rank; rank r renders frame step*N+r",
+                       "rays_per_step_per_gpu": int(n_rays_1),
+                       "step": (f"{args.spp_per_step} frame(s) of ONE image tile-sharded over the ranks (64-pixel blocks round-robin)" if image_mode
+                                else "one frame (1 spp) of the full image per rank; rank r renders frame step*N+r"),
                        "integrator": args.integrator, "accel": args.accel, "l2": "256 MiB flush between timed steps", "cpu_affinity": affinity,
-                       "parallelism": f"frames dealt round-robin over {world} GPU(s); one NCCL reduce of the accumulators at the end"},
-            "spp_per_s": args.steps * world / (ms_total_max * 1e-3), "msamples_per_s": samples_all / (ms_total_max * 1e-3) / 1e6,
+                       "parallelism": (f"image tiles over {world} GPU(s); the gather is fused into the resolve kernel (stores into every rank's image "
+                                       f"over NVLink peer memory), no collective" if image_mode
+                                       else f"frames dealt round-robin over {world} GPU(s); one NCCL reduce of the accumulators at the end")},
+            "spp_per_s": args.steps * (args.spp_per_step if image_mode else world) / (ms_total_max * 1e-3), "msamples_per_s": samples_all / (ms_total_max * 1e-3) / 1e6,
             "exchange_ms": ms_exchange, "bvh_build_s": build_s, "sm_count": sm_count,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(prof["kernel_launches"]),
             "roofline": roof, "cpu_baseline": cpu,
@@ -503,6 +529,15 @@ def main():
         if ab:
             line["ab"] = ab
         print(json.dumps(line), flush=True)
+    if image_mode:
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        for b in peers:
+            b.close()
+        if world > 1:
+            dist.barrier()
+        full.close()
     frame.close()
     scene.close()
     dev.close()
