@@ -260,3 +260,32 @@ def test_two_rank_gloo_shard_and_gather(ob, cornell, w, h):
     f0, _, _ = ob.render(ob.default_params(w, h, first_frame=0, n_frames=1, mode=3, accum=1, max_depth=4), tris, mats)
     f1, _, _ = ob.render(ob.default_params(w, h, first_frame=1, n_frames=1, mode=3, accum=1, max_depth=4), tris, mats)
     assert acc_bytes == (f0 + f1).tobytes()
+
+
+def test_bench_reference_arm_runs_without_gpu():
+    """bench.py --impl reference times the oracle port on the host cores and prints the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("c2")
+
+
+def test_bench_refuses_without_gpu():
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    if torch.cuda.is_available():
+        pytest.skip("needs a CPU-only host")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
