@@ -228,6 +228,8 @@ int ptb_trace(ptb_device* dev, ptb_scene* scene, int accel, int any_hit, int n_r
               uint32_t* out_visits, uint32_t* out_tests);
 int ptb_test_sincos(ptb_device* dev, const float* x, int n, float* s, float* c);
 int ptb_test_pow(ptb_device* dev, const float* x, int n, float y, float* out);
+/* the branch-reduced IEEE helpers of the kernels: out6n = [1/x | sqrt(x) | safe reciprocal | normalize(x, x/2, 2x).xyz] */
+int ptb_test_ieee(ptb_device* dev, const float* x, int n, float* out6n);
 int ptb_test_rng(ptb_device* dev, uint32_t gid, uint32_t frame, int n, uint32_t* states, float* values);
 int ptb_test_camera(ptb_device* dev, int width, int height, int frame, int n, const int32_t* gids, float* o,
                     float* d, uint32_t* seeds);

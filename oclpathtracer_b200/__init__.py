@@ -96,7 +96,7 @@ EXPORTS = [
     "ptb_render_params_default", "ptb_render_local_pixels", "ptb_render", "ptb_render_host",
     "ptb_buffer_ipc_export", "ptb_buffer_ipc_import", "ptb_render_gather",
     "ptb_render_host_async", "ptb_job_wait", "ptb_host_alloc", "ptb_host_free", "ptb_trace",
-    "ptb_device_profile", "ptb_device_profile_read", "ptb_device_set_tuning", "ptb_test_sincos", "ptb_test_pow", "ptb_test_rng", "ptb_test_camera",
+    "ptb_device_profile", "ptb_device_profile_read", "ptb_device_set_tuning", "ptb_test_sincos", "ptb_test_pow", "ptb_test_ieee", "ptb_test_rng", "ptb_test_camera",
 ]
 
 
@@ -448,6 +448,14 @@ class Device:
         o = np.empty_like(x)
         _check(lib().ptb_test_pow(self._h, _p(x), x.size, C.c_float(y), _p(o)))
         return o
+
+    def test_ieee(self, x):
+        """-> dict(rcp, sqrt, safe_rcp, nx, ny, nz) of the kernels' branch-reduced IEEE helpers applied to x."""
+        x = np.ascontiguousarray(x, np.float32)
+        o = np.empty(6 * x.size, np.float32)
+        _check(lib().ptb_test_ieee(self._h, _p(x), x.size, _p(o)))
+        o = o.reshape(6, x.size)
+        return dict(rcp=o[0], sqrt=o[1], safe_rcp=o[2], nx=o[3], ny=o[4], nz=o[5])
 
     def test_rng(self, gid, frame, n):
         st, va = np.empty(n, np.uint32), np.empty(n, np.float32)

@@ -1334,6 +1334,21 @@ extern "C" int ptb_test_pow(ptb_device* dev, const float* x, int n, float y, flo
     return PTB_OK;
 }
 
+extern "C" int ptb_test_ieee(ptb_device* dev, const float* x, int n, float* out6n) {
+    if (!dev || !x || !out6n || n < 0) return fail(PTB_E_INVALID, "ptb_test_ieee: bad arguments");
+    if (n == 0) return PTB_OK;
+    if (set_device(dev)) return PTB_E_CUDA;
+    DevArr<float> dx, dout;
+    int rc;
+    if ((rc = dx.alloc(n)) || (rc = dout.alloc(6 * size_t(n)))) return rc;
+    CU_TRY(cudaMemcpyAsync(dx.p, x, 4 * size_t(n), cudaMemcpyHostToDevice, dev->stream));
+    ptd::k_test_ieee<<<(n + 255) / 256, 256, 0, dev->stream>>>(dx.p, n, dout.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out6n, dout.p, 24 * size_t(n), cudaMemcpyDeviceToHost, dev->stream));
+    CU_TRY(cudaStreamSynchronize(dev->stream));
+    return PTB_OK;
+}
+
 extern "C" int ptb_test_rng(ptb_device* dev, uint32_t gid, uint32_t frame, int n, uint32_t* states, float* values) {
     if (!dev || !states || !values || n < 0) return fail(PTB_E_INVALID, "ptb_test_rng: bad arguments");
     if (n == 0) return PTB_OK;

@@ -546,6 +546,17 @@ __global__ void k_test_pow(const float* x, int n, float y, float* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = det_pow(x[i], y);
 }
+// out[0..n) = rcp_rn(x), out[n..2n) = sqrt_rn(x), out[2n..3n) = safe_rcp3(x,x,x).x, out[3n..6n) = normalize(x, 0.5x, 2x)
+__global__ void k_test_ieee(const float* x, int n, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    out[i] = rcp_rn(v);
+    out[(size_t)n + i] = sqrt_rn(v);
+    out[2 * (size_t)n + i] = safe_rcp3(mk(v, v, v)).x;
+    const V3 u = normalize(mk(v, 0.5f * v, 2.0f * v));
+    out[3 * (size_t)n + i] = u.x; out[4 * (size_t)n + i] = u.y; out[5 * (size_t)n + i] = u.z;
+}
 __global__ void k_test_rng(uint32_t gid, uint32_t frame, int n, uint32_t* states, float* values) {
     if (blockIdx.x || threadIdx.x) return;
     uint32_t seed = gid + hash_uint32(frame);

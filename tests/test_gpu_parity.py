@@ -863,3 +863,40 @@ def test_render_gather_over_ipc(pt):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("identical=True") == 4, r.stdout
+
+
+def test_ieee_helpers_bit_exact(dev):
+    """rcp_rn / sqrt_rn / safe_rcp3 / normalize issue the IEEE refinement sequence without the compiler's range dispatch
+    where the operand range allows it and the generic operator elsewhere: the results must be the IEEE results (numpy
+    float32 division and sqrt are correctly rounded) for every magnitude, sign, zero, denormal, inf and NaN."""
+    rng = np.random.default_rng(1234)
+    n = 1 << 21
+    mag = np.exp2(rng.uniform(-149, 128, n)).astype(np.float32)           # log-uniform over the whole float range
+    x = (mag * rng.choice(np.float32([-1, 1]), n)).astype(np.float32)
+    edge = np.float32([0.0, -0.0, 1e-30, 1.0000001e-30, 9.999999e-31, 1e30, 9.999999e29, 1.0000001e30, 1e-20, 1.0000001e-20,
+                       9.999999e-21, np.inf, -np.inf, np.nan, 1.17549435e-38, 1e-45, 3.4028235e38, 1.0, 2.0, 0.5, 3.0, 1e-8])
+    edge = np.concatenate([edge, -edge])
+    bits_all = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32).view(np.float32)  # uniform over bit patterns
+    x = np.concatenate([x, edge, bits_all, rng.uniform(0, 1, n).astype(np.float32)])
+    got = dev.test_ieee(x)
+    with np.errstate(all="ignore"):
+        one = np.float32(1.0)
+        want_rcp = one / x
+        want_sqrt = np.sqrt(x)
+        a = np.abs(x)
+        want_safe = np.where(a > np.float32(1e-20), one / x, np.where(np.signbit(x), np.float32(-1e20), np.float32(1e20))).astype(np.float32)
+        vx, vy, vz = x, np.float32(0.5) * x, np.float32(2.0) * x
+        dd = (vx * vx + vy * vy) + vz * vz
+        inv = one / np.sqrt(dd)
+        want_n = [vx * inv, vy * inv, vz * inv]
+
+    def same(g, w, name):
+        g, w = np.asarray(g, np.float32), np.asarray(w, np.float32)
+        ok = (g.view(np.uint32) == w.view(np.uint32)) | (np.isnan(g) & np.isnan(w))  # NaN payloads are not part of the contract
+        assert ok.all(), (name, x[~ok][:5], g[~ok][:5], w[~ok][:5])
+
+    same(got["rcp"], want_rcp, "rcp")
+    same(got["sqrt"], want_sqrt, "sqrt")
+    same(got["safe_rcp"], want_safe, "safe_rcp")
+    for g, w, nme in zip((got["nx"], got["ny"], got["nz"]), want_n, "xyz"):
+        same(g, w, "normalize." + nme)
