@@ -389,12 +389,16 @@ def main():
         mp.array[...] = mats
         outs = [pt.PinnedArray((npix, 4), np.float32), pt.PinnedArray((npix, 4), np.float32)]
 
-        def e2e_loop(pipelined):
+        outs8 = [pt.PinnedArray((npix, 3), np.uint8), pt.PinnedArray((npix, 3), np.uint8)]
+
+        def e2e_loop(pipelined, rgb8=False):
             rays = 0
             prev = None
+            dst = outs8 if rgb8 else outs
+            extra = {"output": pt.OUTPUT_RGB8} if rgb8 else {}
             t0 = time.perf_counter()
             for i in range(args.steps):
-                job = dev2.render_host_async(tp.array, mp.array, params(i * world + rank), outs[i & 1].array)
+                job = dev2.render_host_async(tp.array, mp.array, params(i * world + rank, **extra), dst[i & 1].array)
                 if not pipelined:
                     dev2.job_wait(job)
                 else:
@@ -415,20 +419,29 @@ def main():
             dist.barrier()
         t_e2e, e2e_rays = e2e_loop(True)
         checksum = float(outs[(args.steps - 1) & 1].array[:, 0].sum())  # the result is really on the host
-        te = torch.tensor([t_e2e, float(e2e_rays), t_sync], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.barrier()
+        e2e_loop(True, rgb8=True)
+        if world > 1:
+            dist.barrier()
+        t_rgb8, _ = e2e_loop(True, rgb8=True)
+        te = torch.tensor([t_e2e, float(e2e_rays), t_sync, t_rgb8], dtype=torch.float64, device="cuda")
         if world > 1:
             a_ = te.clone(); dist.all_reduce(a_, op=dist.ReduceOp.MAX)
             b_ = te.clone(); dist.all_reduce(b_, op=dist.ReduceOp.SUM)
-            t_e2e, e2e_rays, t_sync = float(a_[0]), float(b_[1]), float(a_[2])
+            t_e2e, e2e_rays, t_sync, t_rgb8 = float(a_[0]), float(b_[1]), float(a_[2]), float(a_[3])
         e2e = {"value": e2e_rays / t_e2e / 1e6, "unit": "Mrays/s",
                "h2d_bytes_per_step": int(tris.nbytes + mats.nbytes), "d2h_bytes_per_step": int(npix * 16),
                "ms_per_step": t_e2e / args.steps * 1e3,
                "synchronous_value": e2e_rays / t_sync / 1e6, "synchronous_ms_per_step": t_sync / args.steps * 1e3,
                "host_checksum": checksum,
+               "rgb8": {"value": e2e_rays / t_rgb8 / 1e6, "unit": "Mrays/s", "d2h_bytes_per_step": int(npix * 3), "ms_per_step": t_rgb8 / args.steps * 1e3,
+                        "note": "same loop with params.output = RGB8: the reference's sqrt/x255/truncate output transform runs on the device "
+                                "and 3 bytes per pixel travel instead of 16"},
                "timing": "host wall clock over K x {ptb_render_host_async (H2D records, render, D2H float4 frame into pinned host memory), "
                          "ptb_job_wait of the previous step}: D2H of step i overlaps the render of step i+1; synchronous_* waits every step. "
                          "Unlike the device-timed steps there is no L2 flush and no accumulate pass between e2e steps, so this can exceed `value`"}
-        for pa in (tp, mp, *outs):
+        for pa in (tp, mp, *outs, *outs8):
             pa.free()
         dev2.close()
 

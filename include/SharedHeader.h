@@ -128,6 +128,11 @@ enum {
 };
 enum { PTB_INTEGRATOR_AUTO = 0, PTB_INTEGRATOR_MEGAKERNEL = 1, PTB_INTEGRATOR_WAVEFRONT = 2 };
 enum { PTB_ACCEL_BVH = 0, PTB_ACCEL_BRUTE = 1 };
+enum {
+    PTB_OUTPUT_FLOAT4 = 0, /* the reference's framebuffer: float4 per pixel                                   */
+    PTB_OUTPUT_RGB8 = 1    /* the reference's final output transform done on the device: sqrt, x255, truncate,
+                              clamp (RaytraceTest.cpp:78-83,:283) -> 3 bytes per pixel, the PPM payload      */
+};
 
 /* Defaults (ptb_render_params_default) equal the reference's hard-coded values:
  * 512x512 (RaytraceTest.cpp:219), BOUNCES 16 (GenerateColors.cl:5), frame
@@ -152,7 +157,9 @@ typedef struct ptb_render_params {
     int32_t shard_index, shard_count, shard_block;
     int32_t collect_stats; /* 1: fill per-pixel hit-ID / visit outputs and counters */
     int32_t frames_per_batch; /* wavefront: samples kept in flight; 0 = auto */
-    int32_t reserved[7];
+    int32_t output;           /* PTB_OUTPUT_*: what ptb_render_host / _async copy to the host (device entry points always
+                                 keep the float4 frame); RGB8 needs accum LINEAR or first_frame 0                       */
+    int32_t reserved[6];
 } ptb_render_params;
 
 /* Ray/test counters (exact integers).  Rays = scene queries (closest or any).

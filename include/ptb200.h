@@ -193,7 +193,11 @@ int ptb_render_host(ptb_device* dev, const ptb_triangle* tris, int n_tris, const
                     const ptb_render_params* params, float* out_rgba, ptb_pixel_stats* out_stats,
                     ptb_counters* counters);
 
-/* Pipelined form: _async enqueues H2D + render + D2H and returns; ptb_job_wait blocks until that job's
+/* With params->output = PTB_OUTPUT_RGB8 both host entry points run the reference's output transform on the device
+ * (RaytraceTest.cpp:78-83,:283; identical bytes to ptb_to_rgb8 of the float4 frame) and out_rgba receives 3 bytes per
+ * local pixel instead of 16 -- the image a PPM writer needs, at a fifth of the PCIe traffic.
+ *
+ * Pipelined form: _async enqueues H2D + render + D2H and returns; ptb_job_wait blocks until that job's
  * frame (and stats) are in the caller's buffers and releases the job.  At most two jobs may be in flight
  * (double buffering: job j's D2H overlaps job j+1's render).  Buffers from ptb_host_alloc are pinned, so the
  * copies go straight to / from them; pageable buffers are staged.  Counters are not available here.      */

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libptb200.so")
 
 MODE_PRIMARY, MODE_AO, MODE_DIRECT, MODE_PATH = 0, 1, 2, 3
 ACCUM_REFERENCE, ACCUM_LINEAR = 0, 1
+OUTPUT_FLOAT4, OUTPUT_RGB8 = 0, 1
 INTEGRATOR_AUTO, INTEGRATOR_MEGAKERNEL, INTEGRATOR_WAVEFRONT = 0, 1, 2
 ACCEL_BVH, ACCEL_BRUTE = 0, 1
 
@@ -55,8 +56,8 @@ class RenderParams(C.Structure):
         ("light_quad", C.c_int32),
         ("light_p1", C.c_float * 3), ("light_ea", C.c_float * 3), ("light_eb", C.c_float * 3),
         ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("shard_block", C.c_int32),
-        ("collect_stats", C.c_int32), ("frames_per_batch", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("collect_stats", C.c_int32), ("frames_per_batch", C.c_int32), ("output", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -370,7 +371,7 @@ class Device:
     def render_host(self, tris, mats, params, out=None, want_stats=False, want_counters=True):
         n = local_pixels(params)
         if out is None:
-            out = np.zeros((n, 4), np.float32)
+            out = np.zeros((n, 3), np.uint8) if params.output == OUTPUT_RGB8 else np.zeros((n, 4), np.float32)
         stats = np.zeros(n, STATS_DTYPE) if want_stats else None
         ctr = Counters() if want_counters else None
         tris = np.ascontiguousarray(tris)

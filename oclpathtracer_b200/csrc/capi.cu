@@ -60,7 +60,7 @@ struct ptb_device {
     cudaStream_t copy_stream = nullptr;               // D2H of finished frames overlaps the next render
     cudaStream_t up_stream = nullptr;                 // H2D of the caller's records, off the render stream's critical path
     struct HostSlot {
-        ptb_buffer* frame = nullptr; ptb_buffer* stats = nullptr;
+        ptb_buffer* frame = nullptr; ptb_buffer* stats = nullptr; ptb_buffer* rgb8 = nullptr;
         void* pin = nullptr; size_t pin_bytes = 0;    // staging when the caller's buffers are pageable
         cudaEvent_t ev_render = nullptr, ev_done = nullptr, ev_up = nullptr;
         bool busy = false;
@@ -213,6 +213,7 @@ extern "C" int ptb_device_destroy(ptb_device* dev) {
     for (auto& sl : dev->slots) {
         if (sl.frame) ptb_buffer_destroy(sl.frame);
         if (sl.stats) ptb_buffer_destroy(sl.stats);
+        if (sl.rgb8) ptb_buffer_destroy(sl.rgb8);
         if (sl.pin) cudaFreeHost(sl.pin);
         if (sl.ev_render) cudaEventDestroy(sl.ev_render);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
@@ -644,6 +645,7 @@ static int validate(const ptb_render_params* p) {
     if (p->accum != PTB_ACCUM_REFERENCE && p->accum != PTB_ACCUM_LINEAR) return fail(PTB_E_INVALID, "ptb_render: bad accum");
     if (p->max_depth < 1 || p->max_depth > 4096) return fail(PTB_E_INVALID, "ptb_render: bad max_depth");
     if (p->mode == PTB_MODE_AO && (p->ao_samples < 1 || p->ao_samples > 4096)) return fail(PTB_E_INVALID, "ptb_render: bad ao_samples");
+    if (p->output != PTB_OUTPUT_FLOAT4 && p->output != PTB_OUTPUT_RGB8) return fail(PTB_E_INVALID, "ptb_render: bad output format %d", p->output);
     if (p->shard_count > 1 && (p->shard_index < 0 || p->shard_index >= p->shard_count || p->shard_block < 1))
         return fail(PTB_E_INVALID, "ptb_render: bad shard spec");
     return PTB_OK;
@@ -898,6 +900,11 @@ extern "C" int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, 
     const int n_local = ptb_render_local_pixels(params);
     const size_t tb = size_t(n_tris) * sizeof(ptb_triangle), mb = size_t(n_mats) * sizeof(ptb_material);
     const size_t fb = size_t(n_local) * 16, sb = out_stats ? size_t(n_local) * sizeof(ptb_pixel_stats) : 0;
+    const bool rgb8 = params->output == PTB_OUTPUT_RGB8;
+    if (rgb8 && params->accum == PTB_ACCUM_REFERENCE && params->first_frame > 0)
+        return fail(PTB_E_INVALID, "ptb_render_host: RGB8 output cannot carry the gamma-space state of accum=REFERENCE across calls "
+                                   "(first_frame > 0); use FLOAT4 output or accum=LINEAR");
+    const size_t cb = rgb8 ? size_t(n_local) * 3 : fb;  // bytes of the image that travel to the host
     const int si = int(dev->jobs_submitted & 1);
     auto& sl = dev->slots[si];
     if (sl.busy) return fail(PTB_E_INVALID, "ptb_render_host_async: more than two jobs in flight; wait for the older one first");
@@ -911,7 +918,8 @@ extern "C" int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, 
     }
     // 1. H2D of the caller's records, as the reference flow uploads tBuffer / materialBuffer (RaytraceTest.cpp:222-246)
     if ((rc = ensure_buffer(dev, &dev->host_tris, tb)) || (rc = ensure_buffer(dev, &dev->host_mats, mb)) ||
-        (rc = ensure_buffer(dev, &sl.frame, fb)) || (sb && (rc = ensure_buffer(dev, &sl.stats, sb))))
+        (rc = ensure_buffer(dev, &sl.frame, fb)) || (sb && (rc = ensure_buffer(dev, &sl.stats, sb))) ||
+        (rgb8 && (rc = ensure_buffer(dev, &sl.rgb8, (cb + 15) & ~size_t(15)))))
         return rc;
     // 2. resident scene (BVH + relaid records) is rebuilt only when the records changed
     uint64_t h = content_hash(tris, tb, 1469598103934665603ull);
@@ -950,12 +958,12 @@ extern "C" int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, 
     // 3. output staging
     sl.direct_frame = is_pinned(out_rgba);
     sl.direct_stats = sb ? is_pinned(out_stats) : true;
-    const size_t need_pin = (sl.direct_frame ? 0 : fb) + (sl.direct_stats ? 0 : sb);
-    if (need_pin && sl.pin_bytes < fb + sb) {
+    const size_t need_pin = (sl.direct_frame ? 0 : cb) + (sl.direct_stats ? 0 : sb);
+    if (need_pin && sl.pin_bytes < cb + sb) {
         if (sl.pin) cudaFreeHost(sl.pin);
         sl.pin = nullptr; sl.pin_bytes = 0;
-        CU_TRY(cudaMallocHost(&sl.pin, fb + sb));
-        sl.pin_bytes = fb + sb;
+        CU_TRY(cudaMallocHost(&sl.pin, cb + sb));
+        sl.pin_bytes = cb + sb;
     }
     // the slot's device frame may still be read by an older copy
     CU_TRY(cudaStreamWaitEvent(dev->stream, sl.ev_done, 0));
@@ -965,15 +973,21 @@ extern "C" int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, 
     if ((rc = render_impl(dev, dev->host_scene, params, static_cast<float4*>(sl.frame->d_ptr), sl.frame->bytes,
                           sb ? static_cast<ptb_pixel_stats*>(sl.stats->d_ptr) : nullptr, sb ? sl.stats->bytes : 0, nullptr)))
         return rc;
+    if (rgb8) {  // the reference's output transform (RaytraceTest.cpp:78-83,:283) on the device: 3 bytes per pixel travel
+        ptd::k_to_rgb8<<<((n_local + 3) / 4 + 255) / 256, 256, 0, dev->stream>>>(static_cast<const float4*>(sl.frame->d_ptr), n_local,
+                                                                                static_cast<uint8_t*>(sl.rgb8->d_ptr));
+        CU_TRY(cudaGetLastError());
+        dev->kernel_launches += 1;
+    }
     CU_TRY(cudaEventRecord(sl.ev_render, dev->stream));
     // 5. D2H on the copy stream
     CU_TRY(cudaStreamWaitEvent(dev->copy_stream, sl.ev_render, 0));
     char* pin = static_cast<char*>(sl.pin);
-    CU_TRY(cudaMemcpyAsync(sl.direct_frame ? (void*)out_rgba : (void*)pin, sl.frame->d_ptr, fb, cudaMemcpyDeviceToHost, dev->copy_stream));
-    if (sb) CU_TRY(cudaMemcpyAsync(sl.direct_stats ? (void*)out_stats : (void*)(pin + fb), sl.stats->d_ptr, sb, cudaMemcpyDeviceToHost, dev->copy_stream));
+    CU_TRY(cudaMemcpyAsync(sl.direct_frame ? (void*)out_rgba : (void*)pin, rgb8 ? sl.rgb8->d_ptr : sl.frame->d_ptr, cb, cudaMemcpyDeviceToHost, dev->copy_stream));
+    if (sb) CU_TRY(cudaMemcpyAsync(sl.direct_stats ? (void*)out_stats : (void*)(pin + cb), sl.stats->d_ptr, sb, cudaMemcpyDeviceToHost, dev->copy_stream));
     CU_TRY(cudaStreamWaitEvent(dev->copy_stream, sl.ev_up, 0));
     CU_TRY(cudaEventRecord(sl.ev_done, dev->copy_stream));
-    sl.busy = true; sl.out = out_rgba; sl.out_stats = out_stats; sl.fb = fb; sl.sb = sb;
+    sl.busy = true; sl.out = out_rgba; sl.out_stats = out_stats; sl.fb = cb; sl.sb = sb;
     ptb_job* job = new ptb_job{dev, si, dev->jobs_submitted};
     dev->jobs_submitted++;
     *job_out = job;

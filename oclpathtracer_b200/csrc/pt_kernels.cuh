@@ -501,6 +501,38 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
     }
 }
 
+// ---- output transform on the device: RaytraceTest.cpp:78-83 f2c applied to sqrtf(v) (:283) ----------------------
+// Same arithmetic as ptb_to_rgb8 (scene.cpp): IEEE sqrt, one multiply, truncation, clamp; out-of-int-range values
+// follow the x86 conversion (INT_MIN -> 0), NaN -> 0.  Four pixels per thread = three 32-bit stores.
+PTD_FI uint32_t f2c_sqrt(float v) {
+    const float a = sqrtf(v) * 255.0f;
+    if (!(a == a)) return 0u;
+    if (a >= 2147483648.0f || a < -2147483648.0f) return 0u;
+    const int b = (int)a;
+    return (uint32_t)(b > 255 ? 255 : (b < 0 ? 0 : b));
+}
+__global__ void __launch_bounds__(256) k_to_rgb8(const float4* frame, int n, uint8_t* rgb) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;  // group of four pixels
+    const int i0 = q * 4;
+    if (i0 >= n) return;
+    if (i0 + 4 <= n) {
+        uint32_t b[12];
+        for (int k = 0; k < 4; ++k) {
+            const float4 v = frame[i0 + k];
+            b[3 * k] = f2c_sqrt(v.x); b[3 * k + 1] = f2c_sqrt(v.y); b[3 * k + 2] = f2c_sqrt(v.z);
+        }
+        uint32_t* dst = reinterpret_cast<uint32_t*>(rgb + (size_t)i0 * 3);  // 12-byte groups from a 16-byte aligned base
+        dst[0] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        dst[1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+        dst[2] = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+    } else {
+        for (int i = i0; i < n; ++i) {
+            const float4 v = frame[i];
+            rgb[(size_t)i * 3] = (uint8_t)f2c_sqrt(v.x); rgb[(size_t)i * 3 + 1] = (uint8_t)f2c_sqrt(v.y); rgb[(size_t)i * 3 + 2] = (uint8_t)f2c_sqrt(v.z);
+        }
+    }
+}
+
 // ---- scene queries on caller-supplied rays (tests) -----------------------------------------------
 
 struct TraceArgs {

@@ -900,3 +900,25 @@ def test_ieee_helpers_bit_exact(dev):
     same(got["safe_rcp"], want_safe, "safe_rcp")
     for g, w, nme in zip((got["nx"], got["ny"], got["nz"]), want_n, "xyz"):
         same(g, w, "normalize." + nme)
+
+
+def test_rgb8_output_equals_host_transform(dev, pt, cornell):
+    """params.output = RGB8: the host entry points deliver sqrt -> x255 -> truncate -> clamp done on the device
+    (RaytraceTest.cpp:78-83,:283); the bytes must equal ptb_to_rgb8 of the float4 frame, also through the async pipeline,
+    for pixel counts that are not a multiple of the kernel's four-pixel groups."""
+    tris, mats = cornell
+    for (w, h), mode, accum in (((97, 53), pt.MODE_PATH, pt.ACCUM_REFERENCE), ((64, 33), pt.MODE_AO, pt.ACCUM_LINEAR),
+                                ((130, 1), pt.MODE_DIRECT, pt.ACCUM_LINEAR), ((1, 1), pt.MODE_PRIMARY, pt.ACCUM_LINEAR)):
+        kw = dict(width=w, height=h, first_frame=0, n_frames=5, mode=mode, accum=accum, max_depth=6)
+        f4, _, _ = dev.render_host(tris, mats, pt.default_params(**kw))
+        u8, _, _ = dev.render_host(tris, mats, pt.default_params(output=pt.OUTPUT_RGB8, **kw))
+        assert u8.dtype == np.uint8 and u8.shape == (w * h, 3)
+        np.testing.assert_array_equal(u8, pt.to_rgb8(f4))
+        pin = pt.PinnedArray((w * h, 3), np.uint8)
+        job = dev.render_host_async(tris, mats, pt.default_params(output=pt.OUTPUT_RGB8, **kw), pin.array)
+        dev.job_wait(job)
+        np.testing.assert_array_equal(pin.array, u8)
+        pin.free()
+    with pytest.raises(pt.PtbError, match="RGB8"):
+        dev.render_host(tris, mats, pt.default_params(width=8, height=8, first_frame=3, n_frames=1, accum=pt.ACCUM_REFERENCE,
+                                                      output=pt.OUTPUT_RGB8))
