@@ -710,7 +710,7 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
 
     // AUTO = the faster integrator as measured on B200.  With 4-wide nodes for
     // shared-memory-resident scenes and path regeneration, the megakernel wins every BASELINE configuration
-    // (C4: 10.7 vs 9.6 Grays/s, C2: 30.7 vs 25.9, C5: 2.9 vs 2.0); the wavefront integrator stays selectable.
+    // (C4: 11.3 vs 10.7 Grays/s, C2: 31.0 vs 25.9, C5: 2.9 vs 2.0); the wavefront integrator stays selectable.
     int integrator = p->integrator;
     if (integrator == PTB_INTEGRATOR_AUTO) integrator = PTB_INTEGRATOR_MEGAKERNEL;
 
