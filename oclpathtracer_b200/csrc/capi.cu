@@ -701,6 +701,16 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
     } else if (p->mode == PTB_MODE_DIRECT) {
         if (int rc = ptb_light_from_quad(scene->host_tris.data(), scene->n_tris, p->light_quad, a.light_p1, a.light_ea, a.light_eb)) return rc;
     }
+    if (p->mode == PTB_MODE_DIRECT) {
+        // |cross(ea, eb)| and its unit vector, spelled as the kernels (and the oracle) spell them per sample: products and
+        // sums rounded one by one (this file is compiled without FMA contraction), IEEE sqrt and division
+        const float* ea = a.light_ea; const float* eb = a.light_eb;
+        const float cx = ea[1] * eb[2] - ea[2] * eb[1], cy = ea[2] * eb[0] - ea[0] * eb[2], cz = ea[0] * eb[1] - ea[1] * eb[0];
+        const float dd = (cx * cx + cy * cy) + cz * cz;
+        a.light_area = std::sqrt(dd);
+        const float inv = 1.0f / std::sqrt(dd);
+        a.light_n[0] = cx * inv; a.light_n[1] = cy * inv; a.light_n[2] = cz * inv;
+    }
     a.shard.index = p->shard_index; a.shard.count = p->shard_count < 1 ? 1 : p->shard_count; a.shard.block = p->shard_block < 1 ? 1 : p->shard_block;
     a.samples = ext_samples ? ext_samples : static_cast<float4*>(dev->samples);
     a.stats = stats ? d_stats : nullptr;

@@ -116,6 +116,7 @@ struct RenderArgs {
     float ao_max_dist;
     int light_quad;
     float light_p1[3], light_ea[3], light_eb[3];
+    float light_n[3], light_area;  // normalize(cross(ea, eb)) and |cross(ea, eb)|: the same for every sample, computed once by the host with the same IEEE operations
     Shard shard;
     float4* samples;            // [frames_in_batch][n_local] radiance (xyz)
     ptb_pixel_stats* stats;     // per local pixel, written for stats_frame only
@@ -276,11 +277,10 @@ PTD_FI V3 sample_direct(const Ctx& c, const RenderArgs& a, Ray r, uint32_t& seed
     const V3 P = add(add(lp, mul(ea, xi1)), mul(eb, xi2));
     const V3 L = sub(P, p);
     const float dist2 = dot(L, L);
-    const float dist = sqrtf(dist2);
-    const V3 wi = normalize(L);
-    const V3 lc = cross(ea, eb);
-    const float area = sqrtf(dot(lc, lc));
-    const V3 nl = normalize(lc);
+    const float dist = sqrt_rn(dist2);
+    const V3 wi = mul(L, rcp_rn(dist));  // == normalize(L): L * (1 / sqrt(dot(L, L)))
+    const float area = a.light_area;
+    const V3 nl = mk(a.light_n[0], a.light_n[1], a.light_n[2]);
     const float cos_s = dot(wi, n);
     const float cos_l = -dot(wi, nl);
     if (cos_s > 0.0f && cos_l > 0.0f) {

@@ -484,11 +484,10 @@ __global__ void __launch_bounds__(128) wf_shade_first(const SceneDev sc, const R
         const V3 Pl = add(add(lp, mul(ea, xi1)), mul(eb, xi2));
         const V3 L = sub(Pl, p);
         const float dist2 = dot(L, L);
-        const float dist = sqrtf(dist2);
-        const V3 wi = normalize(L);
-        const V3 lc = cross(ea, eb);
-        const float area = sqrtf(dot(lc, lc));
-        const V3 nl = normalize(lc);
+        const float dist = sqrt_rn(dist2);
+        const V3 wi = mul(L, rcp_rn(dist));  // == normalize(L)
+        const float area = a.light_area;
+        const V3 nl = mk(a.light_n[0], a.light_n[1], a.light_n[2]);
         const float cos_s = dot(wi, nrm);
         const float cos_l = -dot(wi, nl);
         if (cos_s > 0.0f && cos_l > 0.0f) {
