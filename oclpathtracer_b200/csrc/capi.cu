@@ -701,6 +701,8 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
     } else if (p->mode == PTB_MODE_DIRECT) {
         if (int rc = ptb_light_from_quad(scene->host_tris.data(), scene->n_tris, p->light_quad, a.light_p1, a.light_ea, a.light_eb)) return rc;
     }
+    a.cam_inv_w = 1.0f / (float)p->width; a.cam_inv_h = 1.0f / (float)p->height;  // GenerateColors.cl:265
+    a.cam_aspect = (float)p->width / (float)p->height;                            // :266
     if (p->mode == PTB_MODE_DIRECT) {
         // |cross(ea, eb)| and its unit vector, spelled as the kernels (and the oracle) spell them per sample: products and
         // sums rounded one by one (this file is compiled without FMA contraction), IEEE sqrt and division

@@ -116,6 +116,7 @@ struct RenderArgs {
     float ao_max_dist;
     int light_quad;
     float light_p1[3], light_ea[3], light_eb[3];
+    float cam_inv_w, cam_inv_h, cam_aspect;  // CamScale of (width, height), computed by the host
     float light_n[3], light_area;  // normalize(cross(ea, eb)) and |cross(ea, eb)|: the same for every sample, computed once by the host with the same IEEE operations
     Shard shard;
     float4* samples;            // [frames_in_batch][n_local] radiance (xyz)
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(128, ((MODE == PTB_MODE_AO || MODE == PTB_MODE
         const int frame = a.first_frame + fi;
         const int gi = gid % a.width, gj = gid / a.width;           // GenerateColors.cl:305-306
         uint32_t seed = (uint32_t)gid + hash_uint32((uint32_t)frame);  // :308
-        const Ray r = generate_ray(gi, gj, a.width, a.height, seed);   // :310
+        const Ray r = generate_ray(gi, gj, CamScale{a.cam_inv_w, a.cam_inv_h, a.cam_aspect}, seed);   // :310
         SampleStats<STATS> st{};
         V3 col;
         if (MODE == PTB_MODE_PRIMARY) col = sample_primary<BVH, SMALL, STATS>(c, r, st, rc, qs);
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(128) k_mega_path_regen(const SceneDev sc, cons
                     const int gid = gid_of_local(a.shard, li);
                     frame = a.first_frame + fi;
                     seed = (uint32_t)gid + hash_uint32((uint32_t)frame);                    // GenerateColors.cl:308
-                    r = generate_ray(gid % a.width, gid / a.width, a.width, a.height, seed);  // :310
+                    r = generate_ray(gid % a.width, gid / a.width, CamScale{a.cam_inv_w, a.cam_inv_h, a.cam_aspect}, seed);  // :310
                     radiance = mk(0.f, 0.f, 0.f);
                     mask = mk(1.f, 1.f, 1.f);
                     depth = 0;

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) wf_generate(const RenderArgs a, const WfB
     const int gid = gid_of_local(a.shard, li);
     const int frame = a.first_frame + fi;
     uint32_t seed = (uint32_t)gid + hash_uint32((uint32_t)frame);          // GenerateColors.cl:308
-    const Ray r = generate_ray(gid % a.width, gid / a.width, a.width, a.height, seed);  // :310
+    const Ray r = generate_ray(gid % a.width, gid / a.width, CamScale{a.cam_inv_w, a.cam_inv_h, a.cam_aspect}, seed);  // :310
     w.q_o[0][slot] = make_float4(r.o.x, r.o.y, r.o.z, __int_as_float((int)slot));
     w.q_d[0][slot] = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(seed));
     w.q_m[0][slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
