@@ -289,3 +289,20 @@ def test_bench_refuses_without_gpu():
         pytest.skip("needs a CPU-only host")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_unmodified_reference_test_over_shim_needs_a_device(pt, tmp_path):
+    """oracle/_ref/adlTest64_ptb200 (the reference's own test sources compiled against the ADL-shaped shim) links
+    libptb200.so and has no CPU path: without a device its fixture cannot allocate one and every case fails."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "adlTest64_ptb200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/adlTest64_ptb200 not built (make -C oracle ref needs the reference tree)")
+    n = C.c_int(-1)
+    if pt.lib().ptb_device_count(C.byref(n)) == 0 and n.value > 0:
+        pytest.skip("a CUDA device is present")
+    ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libptb200.so" in ldd and "libOpenCL" not in ldd
+    env = dict(os.environ, PTB_REF_WORKDIR=str(tmp_path / "ref"))
+    r = subprocess.run([exe, "--gtest_filter=DeviceTest.initialize:DeviceTest.deviceInfo"], capture_output=True, text=True, timeout=60, env=env)
+    assert r.returncode != 0 and "FAILED" in r.stdout
