@@ -306,3 +306,18 @@ def test_unmodified_reference_test_over_shim_needs_a_device(pt, tmp_path):
     env = dict(os.environ, PTB_REF_WORKDIR=str(tmp_path / "ref"))
     r = subprocess.run([exe, "--gtest_filter=DeviceTest.initialize:DeviceTest.deviceInfo"], capture_output=True, text=True, timeout=60, env=env)
     assert r.returncode != 0 and "FAILED" in r.stdout
+
+
+def test_bench_reference_arm_under_torchrun():
+    """Launched like the driver does for N>1: rank 0 alone runs and prints the line, the other ranks exit 0 silently."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29641", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
