@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--smem-nodes", type=int, default=0, help="BVH nodes staged in shared memory (0 = default)")
     ap.add_argument("--max-leaf", type=int, default=0, help="BVH max triangles per leaf (0 = default)")
     ap.add_argument("--sah-traverse", type=float, default=0.0, help="SAH node-visit cost (0 = default 1.2)")
+    ap.add_argument("--force-width", type=int, default=0, help="force the scene form: 1 FLAT, 4 4-wide, 2 binary (0 = the library's pick)")
     ap.add_argument("--sharding", choices=["frames", "image"], default="frames",
                     help="frames (default): rank r renders whole frames = r mod N, weak scaling, one NCCL reduce at the end; "
                          "image: every step is ONE image tile-sharded over the ranks (64-pixel blocks round-robin) with the gather "
@@ -284,8 +285,9 @@ def main():
     tris, mats, light = load_scene(pt, wl)
     t0 = time.perf_counter()
     bp = None
-    if args.smem_nodes or args.max_leaf or args.sah_traverse:
+    if args.smem_nodes or args.max_leaf or args.sah_traverse or args.force_width:
         bp = pt.bvh_params()
+        bp.force_width = args.force_width
         if args.sah_traverse:
             bp.traverse_cost = args.sah_traverse
         if args.smem_nodes:
@@ -451,7 +453,7 @@ def main():
     nodes_per_ray = stat_ctr["nodes"] / max(1, stat_ctr["rays_closest"] + stat_ctr["rays_any"])
     tests_per_ray = stat_ctr["tri_tests"] / max(1, stat_ctr["rays_closest"] + stat_ctr["rays_any"])
     q_bytes_per_ray = 16.0 * npix / n_rays_1  # one float4 radiance sample written per pixel-frame by the integrator
-    node_bytes = 128 if scene.info()["width"] == 4 else 64
+    node_bytes = {4: 128, 2: 64, 1: 32}[scene.info()["width"]]
     bytes_per_ray = nodes_per_ray * node_bytes + tests_per_ray * 48 + q_bytes_per_ray
     integ_ms = prof["integrator_ms"] / max(1, prof["batches"])
     rays_per_launch = n_rays_1 / max(1, prof["batches"] / args.steps)
@@ -484,13 +486,14 @@ def main():
         # stage counts of the BVH path at reduced size -> fp32 lane-ops per ray (SURVEY 8d formula)
         otris, omats = ob.load_model(SCENE)
         if not wl.get("tess"):
-            b = pt.build_bvh_host(otris)
+            b = ob.build_bvh(otris, width=scene.info()["width"])
             bvh, _keep = ob.make_bvh(b["nodes"], b["tri_order"])
             op = ob.default_params(256, 256, n_frames=1, mode=wl["mode"], accum=1, use_bvh=1, ao_samples=wl.get("ao_samples", 16),
                                    max_depth=wl.get("max_depth", 16), light_p1=light[0], light_ea=light[1], light_eb=light[2])
             _, _, oc = ob.render(op, otris, omats, bvh=bvh)
             nr = oc["rays_closest"] + oc["rays_any"]
-            flops_per_ray = ((node_bytes // 32) * oc["nodes"] * 24 + oc["tri_tests"] * 14 + oc["tri_u"] * 10 + oc["tri_v"] * 15 + oc["tri_t"] * 6 + oc["tri_accept"] * 40) / nr
+            boxes = oc["nodes"] * (node_bytes // 32) if scene.info()["width"] != 1 else nr * scene.info()["n_nodes"]  # FLAT: every leaf box, every ray
+            flops_per_ray = (boxes * 24 + oc["tri_tests"] * 14 + oc["tri_u"] * 10 + oc["tri_v"] * 15 + oc["tri_t"] * 6 + oc["tri_accept"] * 40) / nr
             sm_mhz = clocks.get("sm_mhz") or sm_max_mhz
             peak_lane_ops = sm_count * 128 * sm_max_mhz * 1e6  # no FMA in the parity build: 1 lane-op per lane per clock
             ach = flops_per_ray * (rays_per_launch / (integ_ms * 1e-3))

@@ -59,7 +59,7 @@ typedef struct ptb_triangle {
  * first = (~ref) >> 3, count = ((~ref) & 7) + 1 into the ordered triangle array; PTB_BVH_EMPTY = unused slot
  * (its box has e = -1e30 and never hits).
  *
- * Two node widths, chosen per scene:
+ * Two node widths (and the FLAT form below), chosen per scene:
  *   ptb_bvh_node   binary, 4 x 128-bit words = 64 B  -- scenes traversed from L2/HBM (fewest bytes and registers
  *                                                        per visit; measured best on the 2M-triangle scene)
  *   ptb_bvh_node4  4-wide, 8 x 128-bit words = 128 B -- scenes that live entirely in shared memory (half as many
@@ -93,6 +93,21 @@ typedef struct ptb_bvh_node4 {
     float e3[3];
     int32_t pad3;
 } ptb_bvh_node4;
+
+/* FLAT form for scenes of <= PTB_FLAT_MAX_LEAVES leaves and <= 64 triangles (the Cornell box: 18 leaves, 36 triangles):
+ * no tree at all -- the leaf slots of the binary tree in leaf order, each with its padded box (centre / half-extent, as
+ * above) and the 64-bit mask of the positions its triangles occupy in the ordered triangle array.  A query slab-tests
+ * EVERY leaf box in straight-line code (all 32 lanes of a warp busy, the records are kernel parameters read as
+ * constant-bank operands), ORs the masks of the boxes it hits, then runs Moller-Trumbore over the set bits.  There is no
+ * stack, no child ordering and no trip-count divergence in the box phase.            */
+typedef struct ptb_bvh_leafbox {
+    float c[3];
+    uint32_t mask_lo; /* word 0: box centre,      triangle positions 0..31 of this leaf */
+    float e[3];
+    uint32_t mask_hi; /* word 1: box half-extent, triangle positions 32..63 */
+} ptb_bvh_leafbox;
+#define PTB_FLAT_MAX_LEAVES 32
+#define PTB_FLAT_MAX_TRIS 64
 
 #define PTB_BVH_WIDTH 4
 #define PTB_MAX_PEERS 7 /* peer images a gathering render can store into (8 GPUs per node) */ /* slots of a ptb_bvh_node4 */
@@ -181,6 +196,7 @@ static_assert(sizeof(ptb_triangle) == 64, "Triangle must be 64 bytes (RaytraceTe
 static_assert(sizeof(ptb_bvh_node) == 64, "binary BVH node must be 64 bytes");
 static_assert(sizeof(ptb_bvh_node4) == 128, "4-wide BVH node must be 128 bytes");
 static_assert(sizeof(ptb_bvh_tri) == 48, "BVH triangle must be 48 bytes");
+static_assert(sizeof(ptb_bvh_leafbox) == 32, "flat leaf box must be 32 bytes");
 #endif
 #endif
 

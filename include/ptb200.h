@@ -129,12 +129,15 @@ typedef struct ptb_bvh_params {
     int32_t n_bins;     /* SAH bins, default 16 */
     int32_t smem_nodes; /* top-of-tree nodes laid out first (BFS) for shared-memory staging, default 1024 */
     float traverse_cost; /* SAH cost of one node visit relative to one triangle test (<= 0: default 1.2) */
-    int32_t reserved[3];
+    int32_t force_width; /* 0 = pick the scene class (below); 1 | 4 | 2 = force the FLAT / 4-wide / binary form (A/B runs and tests;
+                            ptb_scene_create fails when the scene does not qualify for the forced form) */
+    int32_t reserved[2];
 } ptb_bvh_params;
 void ptb_bvh_params_default(ptb_bvh_params* p);
 
 /* host-only build (no device needed): returns malloc'd arrays, release with ptb_free.  width = 2: ptb_bvh_node
- * records; width = 4: ptb_bvh_node4 records (the same tree collapsed; built for scenes of <= 2048 triangles) */
+ * records; width = 4: ptb_bvh_node4 records (the same tree collapsed; built for scenes of <= 2048 triangles);
+ * width = 1: ptb_bvh_leafbox records (the FLAT form: <= 32 leaves and <= 64 triangles) */
 int ptb_bvh_build_host(const ptb_triangle* tris, int n_tris, const ptb_bvh_params* bvh_params, int width, void** nodes,
                        int* n_nodes, int32_t** tri_order, ptb_bvh_tri** ordered_tris, int* depth, int* smem_nodes);
 
@@ -146,8 +149,12 @@ int ptb_scene_create_gpu(ptb_device* dev, const ptb_triangle* tris, int n_tris, 
                          const ptb_bvh_params* bvh_params /* NULL = default */, ptb_scene** out);
 int ptb_scene_destroy(ptb_scene* scene);
 int ptb_scene_info(ptb_scene* scene, int* n_nodes, int* n_tris, int* depth, int* smem_nodes);
-/* node width of the resident tree: 4 (ptb_bvh_node4, scenes that fit a 32 KB shared-memory budget) or 2 */
+/* form of the resident scene: 1 (FLAT: ptb_bvh_leafbox records, scenes of <= 32 leaves and <= 64 triangles), 4
+ * (ptb_bvh_node4, scenes that fit a 32 KB shared-memory budget) or 2 (ptb_bvh_node, traversed from L2/HBM) */
 int ptb_scene_bvh_width(ptb_scene* scene);
+/* form a render of `mode` (PTB_MODE_*) walks: a FLAT scene keeps its 4-wide tree resident too and uses it where the rays of a
+ * warp are coherent (PTB_MODE_DIRECT); results are identical, the visit statistics follow the form */
+int ptb_scene_mode_width(ptb_scene* scene, int mode);
 /* host copies of the built tree (n_nodes records of the scene's width), for structural validation and tests */
 int ptb_scene_copy_bvh(ptb_scene* scene, void* nodes, int32_t* tri_order);
 

@@ -39,6 +39,9 @@ NODE4_DTYPE = np.dtype(  # 4-wide node, 128 bytes (ptb_bvh_node4)
         ("c3", "<f4", 3), ("pad2", "<i4"), ("e3", "<f4", 3), ("pad3", "<i4"),
     ]
 )
+LEAFBOX_DTYPE = np.dtype(  # FLAT form, 32 bytes (ptb_bvh_leafbox)
+    [("c", "<f4", 3), ("mask_lo", "<u4"), ("e", "<f4", 3), ("mask_hi", "<u4")]
+)
 STATS_DTYPE = np.dtype(
     [
         ("tri", "<i4"), ("quad", "<i4"), ("t_bits", "<u4"), ("visits_primary", "<u4"),
@@ -72,7 +75,7 @@ class Counters(C.Structure):
 
 class BvhParams(C.Structure):
     _fields_ = [("max_leaf", C.c_int32), ("pad_rel", C.c_float), ("n_bins", C.c_int32), ("smem_nodes", C.c_int32),
-                ("traverse_cost", C.c_float), ("reserved", C.c_int32 * 3)]
+                ("traverse_cost", C.c_float), ("force_width", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class Int4(C.Structure):
@@ -93,7 +96,7 @@ EXPORTS = [
     "ptb_buffer_map", "ptb_buffer_unmap", "ptb_buffer_clear", "ptb_buffer_device_ptr", "ptb_buffer_size",
     "ptb_kernel_get", "ptb_kernel_set_int", "ptb_launch1d", "ptb_launch_serialize", "ptb_launch_deserialize", "ptb_load_model", "ptb_tessellate",
     "ptb_light_from_quad", "ptb_free", "ptb_to_rgb8", "ptb_write_ppm", "ptb_bvh_params_default",
-    "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_create_gpu", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_bvh_width", "ptb_scene_copy_bvh",
+    "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_create_gpu", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_bvh_width", "ptb_scene_mode_width", "ptb_scene_copy_bvh",
     "ptb_render_params_default", "ptb_render_local_pixels", "ptb_render", "ptb_render_host",
     "ptb_buffer_ipc_export", "ptb_buffer_ipc_import", "ptb_render_gather",
     "ptb_render_host_async", "ptb_job_wait", "ptb_host_alloc", "ptb_host_free", "ptb_trace",
@@ -136,6 +139,7 @@ def lib():
         L.ptb_device_memory.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ptb_bvh_build_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6
         L.ptb_scene_bvh_width.argtypes = [C.c_void_p]
+        L.ptb_scene_mode_width.argtypes = [C.c_void_p, C.c_int]
         L.ptb_scene_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptb_scene_create_gpu.argtypes = L.ptb_scene_create.argtypes
         L.ptb_scene_info.argtypes = [C.c_void_p] + [C.c_void_p] * 4
@@ -237,19 +241,20 @@ BVH_TRI_DTYPE = np.dtype(
 def build_bvh_host(tris, params=None, width=None):
     """Host-only BVH build (no GPU): dict(nodes, tri_order, ordered_tris, depth, smem_nodes, width).
 
-    width 4 -> NODE4_DTYPE records (what a shared-memory-resident scene uses), 2 -> NODE_DTYPE;
-    None picks like ptb_scene_create does for the Cornell-sized scenes of the tests (4 when <= 256 triangles).
+    width 1 -> LEAFBOX_DTYPE records (the FLAT form of scenes with <= 32 leaves and <= 64 triangles), 4 -> NODE4_DTYPE
+    records (what a shared-memory-resident scene uses), 2 -> NODE_DTYPE;
+    None picks like ptb_scene_create does for the scenes of the tests (1 when <= 64 triangles, 4 when <= 256, else 2).
     """
     L = lib()
     tris = np.ascontiguousarray(tris)
     if width is None:
-        width = 4 if len(tris) <= 256 else 2
+        width = 1 if len(tris) <= 64 else 4 if len(tris) <= 256 else 2
     nodes, order, otris = C.c_void_p(), C.c_void_p(), C.c_void_p()
     nn, depth, sn = C.c_int(), C.c_int(), C.c_int()
     _check(L.ptb_bvh_build_host(_p(tris), len(tris), C.byref(params) if params is not None else None, width,
                                 C.byref(nodes), C.byref(nn), C.byref(order), C.byref(otris), C.byref(depth),
                                 C.byref(sn)))
-    dt = NODE4_DTYPE if width == 4 else NODE_DTYPE
+    dt = {1: LEAFBOX_DTYPE, 4: NODE4_DTYPE, 2: NODE_DTYPE}[width]
     try:
         res = {
             "width": width,
@@ -539,9 +544,13 @@ class Scene:
         return {"n_nodes": a.value, "n_tris": b.value, "depth": c.value, "smem_nodes": d.value,
                 "width": lib().ptb_scene_bvh_width(self._h)}
 
+    def mode_width(self, mode):
+        """form (1 FLAT, 4, 2) a render of `mode` walks"""
+        return lib().ptb_scene_mode_width(self._h, mode)
+
     def bvh(self):
         inf = self.info()
-        nodes = np.zeros(inf["n_nodes"], NODE4_DTYPE if inf["width"] == 4 else NODE_DTYPE)
+        nodes = np.zeros(inf["n_nodes"], {1: LEAFBOX_DTYPE, 4: NODE4_DTYPE, 2: NODE_DTYPE}[inf["width"]])
         order = np.zeros(inf["n_tris"], np.int32)
         _check(lib().ptb_scene_copy_bvh(self._h, _p(nodes), _p(order)))
         return nodes, order

@@ -272,6 +272,29 @@ int build_bvh(const ptb_triangle* tris, int n_tris, const ptb_bvh_params& params
     out->depth = depth;
     out->smem_nodes = bfs_count;
 
+    if (n_tris <= PTB_FLAT_MAX_TRIS) {  // tiny scenes also get the FLAT form: every leaf slot with its box and triangle mask
+        std::vector<ptb_bvh_leafbox> flat;
+        bool fits = true;
+        // leaf order == depth-first order with slot 0 first
+        std::vector<std::pair<int32_t, int>> st;
+        if (n_tris > 1) st.push_back({0, 1});  // the one-triangle root repeats its leaf in both slots
+        st.push_back({0, 0});
+        while (!st.empty()) {
+            const auto [ni, slot] = st.back();
+            st.pop_back();
+            const int32_t r = B.nodes[ni].child[slot];
+            if (r >= 0) { st.push_back({r, 1}); st.push_back({r, 0}); continue; }
+            if (int(flat.size()) >= PTB_FLAT_MAX_LEAVES) { fits = false; break; }
+            const int first = PTB_BVH_LEAF_FIRST(r), count = PTB_BVH_LEAF_COUNT(r);
+            const uint64_t m = ((uint64_t(1) << count) - 1) << first;
+            ptb_bvh_leafbox lb;
+            for (int a = 0; a < 3; ++a) centre_extent(B.nodes[ni].box[slot].lo[a] - pad, B.nodes[ni].box[slot].hi[a] + pad, &lb.c[a], &lb.e[a]);
+            lb.mask_lo = uint32_t(m); lb.mask_hi = uint32_t(m >> 32);
+            flat.push_back(lb);
+        }
+        if (fits) out->flat = flat;
+    }
+
     if (n_tris <= 2048) {  // small scenes also get the 4-wide form (shared-memory-resident traversal)
         // collapse the binary tree into 4-wide nodes: start from a node's two children and keep replacing the
         // internal child with the largest box (ties: lowest slot) by its own two children, in place, until four

@@ -69,7 +69,7 @@ struct ptb_device {
         bool direct_frame = false, direct_stats = false;
     } slots[2];
     uint64_t jobs_submitted = 0;
-    int tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // experiment knobs (ptb_device_set_tuning)
+    int tune[16] = {0};  // experiment knobs (ptb_device_set_tuning)
     // measurement
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;   // triples: before integrator, after integrator, after resolve
@@ -112,11 +112,13 @@ struct ptb_scene {
     BuiltBvh bvh;
     int n_tris = 0, n_mats = 0;
     float4* d_nodes = nullptr;
+    float4* d_nodes4 = nullptr;           // FLAT scenes also keep their 4-wide tree resident: coherent-ray modes use it (mode_class)
     float4* d_tris = nullptr;
     float4* d_tris_orig = nullptr;
     float4* d_mats = nullptr;
-    bool small = false;
-    int width = 2;                        // 4: ptb_bvh_node4 records (small scenes), 2: ptb_bvh_node
+    bool small = false;                   // triangles and materials are staged in shared memory (FLAT and 4-wide scenes)
+    int cls = ptd::PTD_LARGE;             // scene class: PTD_LARGE | PTD_SMALL4 | PTD_FLAT
+    int width = 2;                        // 1: ptb_bvh_leafbox records (FLAT), 4: ptb_bvh_node4 records (small scenes), 2: ptb_bvh_node
     int n_nodes = 0, depth = 0, bfs_nodes = 0;
     int* d_order = nullptr;               // GPU-built scenes: BVH position -> caller index (device)
     bool host_copy_valid = true;          // false until a GPU-built tree has been downloaded
@@ -360,7 +362,7 @@ extern "C" int ptb_scene_destroy(ptb_scene* s) {
     if (!s) return PTB_OK;
     set_device(s->dev);
     cudaStreamSynchronize(s->dev->stream);
-    for (void* p : {(void*)s->d_nodes, (void*)s->d_tris, (void*)s->d_tris_orig, (void*)s->d_mats, (void*)s->d_order})
+    for (void* p : {(void*)s->d_nodes, (void*)s->d_nodes4, (void*)s->d_tris, (void*)s->d_tris_orig, (void*)s->d_mats, (void*)s->d_order})
         if (p) cudaFree(p);
     delete s;
     return PTB_OK;
@@ -392,8 +394,17 @@ extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n
     }
     // scene class: everything (4-wide nodes, triangles, materials) fits a 32 KB shared-memory budget -> SMALL
     const size_t staged4 = s->bvh.nodes4.size() * sizeof(ptb_bvh_node4) + size_t(n_tris) * 48 + size_t(n_mats) * 32;
-    s->small = !s->bvh.nodes4.empty() && staged4 <= 32 * 1024 && int(s->bvh.nodes4.size()) == s->bvh.smem_nodes4;
-    if (s->small) { s->width = 4; s->n_nodes = int(s->bvh.nodes4.size()); s->depth = s->bvh.depth4; s->bfs_nodes = s->bvh.smem_nodes4; }
+    const bool can4 = !s->bvh.nodes4.empty() && staged4 <= 32 * 1024 && int(s->bvh.nodes4.size()) == s->bvh.smem_nodes4;
+    const bool can_flat = !s->bvh.flat.empty();  // <= 32 leaves and <= 64 triangles: no tree, leaf boxes as kernel parameters
+    if ((bp.force_width == 1 && !can_flat) || (bp.force_width == 4 && !can4) || (bp.force_width != 0 && bp.force_width != 1 && bp.force_width != 2 && bp.force_width != 4)) {
+        delete s;
+        return fail(PTB_E_INVALID, "ptb_scene_create: the scene does not qualify for force_width = %d", bp.force_width);
+    }
+    s->cls = bp.force_width == 1 ? ptd::PTD_FLAT : bp.force_width == 4 ? ptd::PTD_SMALL4 : bp.force_width == 2 ? ptd::PTD_LARGE
+             : can_flat ? ptd::PTD_FLAT : can4 ? ptd::PTD_SMALL4 : ptd::PTD_LARGE;
+    s->small = s->cls != ptd::PTD_LARGE;
+    if (s->cls == ptd::PTD_FLAT) { s->width = 1; s->n_nodes = int(s->bvh.flat.size()); s->depth = 1; s->bfs_nodes = s->n_nodes; }
+    else if (s->cls == ptd::PTD_SMALL4) { s->width = 4; s->n_nodes = int(s->bvh.nodes4.size()); s->depth = s->bvh.depth4; s->bfs_nodes = s->bvh.smem_nodes4; }
     else { s->width = 2; s->n_nodes = int(s->bvh.nodes.size()); s->depth = s->bvh.depth; s->bfs_nodes = s->bvh.smem_nodes; }
     if (set_device(dev)) { delete s; return PTB_E_CUDA; }
     auto up = [&](float4** d, const void* h, size_t bytes) -> int {
@@ -401,8 +412,12 @@ extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n
         CU_TRY(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, dev->stream));
         return PTB_OK;
     };
-    if ((rc = s->small ? up(&s->d_nodes, s->bvh.nodes4.data(), s->bvh.nodes4.size() * sizeof(ptb_bvh_node4))
-                       : up(&s->d_nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptb_bvh_node))) ||
+    std::vector<ptb_bvh_leafbox> flat_padded = s->bvh.flat;  // staged count is even: pad with a box that never hits
+    if (flat_padded.size() & 1) flat_padded.push_back(ptb_bvh_leafbox{{0.f, 0.f, 0.f}, 0u, {-1e30f, -1e30f, -1e30f}, 0u});
+    if ((rc = s->cls == ptd::PTD_FLAT     ? up(&s->d_nodes, flat_padded.data(), flat_padded.size() * sizeof(ptb_bvh_leafbox))
+              : s->cls == ptd::PTD_SMALL4 ? up(&s->d_nodes, s->bvh.nodes4.data(), s->bvh.nodes4.size() * sizeof(ptb_bvh_node4))
+                                          : up(&s->d_nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptb_bvh_node))) ||
+        (s->cls == ptd::PTD_FLAT && can4 && bp.force_width == 0 && (rc = up(&s->d_nodes4, s->bvh.nodes4.data(), s->bvh.nodes4.size() * sizeof(ptb_bvh_node4)))) ||
         (rc = up(&s->d_tris, s->bvh.tris.data(), s->bvh.tris.size() * 48)) ||
         (rc = up(&s->d_tris_orig, orig.data(), orig.size() * 48)) || (rc = up(&s->d_mats, m.data(), m.size() * 16))) {
         ptb_scene_destroy(s);
@@ -470,26 +485,28 @@ extern "C" int ptb_bvh_build_host(const ptb_triangle* tris, int n_tris, const pt
                                   void** nodes, int* n_nodes, int32_t** tri_order, ptb_bvh_tri** ordered_tris,
                                   int* depth, int* smem_nodes) {
     if (!tris || !nodes || !n_nodes || !tri_order) return fail(PTB_E_INVALID, "ptb_bvh_build_host: null argument");
-    if (width != 2 && width != 4) return fail(PTB_E_INVALID, "ptb_bvh_build_host: width must be 2 or 4");
+    if (width != 2 && width != 4 && width != 1) return fail(PTB_E_INVALID, "ptb_bvh_build_host: width must be 1, 2 or 4");
     ptb_bvh_params bp;
     if (bvh_params) bp = *bvh_params; else ptb_bvh_params_default(&bp);
     BuiltBvh b;
     if (int rc = build_bvh(tris, n_tris, bp, &b)) return rc;
     if (width == 4 && b.nodes4.empty()) return fail(PTB_E_INVALID, "ptb_bvh_build_host: 4-wide trees are built for <= 2048 triangles");
-    const size_t node_bytes = width == 4 ? b.nodes4.size() * sizeof(ptb_bvh_node4) : b.nodes.size() * sizeof(ptb_bvh_node);
+    if (width == 1 && b.flat.empty()) return fail(PTB_E_INVALID, "ptb_bvh_build_host: the FLAT form needs <= 32 leaves and <= 64 triangles");
+    const size_t node_bytes = width == 1 ? b.flat.size() * sizeof(ptb_bvh_leafbox)
+                              : width == 4 ? b.nodes4.size() * sizeof(ptb_bvh_node4) : b.nodes.size() * sizeof(ptb_bvh_node);
     *nodes = std::malloc(node_bytes);
     *tri_order = static_cast<int32_t*>(std::malloc(b.tri_order.size() * sizeof(int32_t)));
     if (!*nodes || !*tri_order) return fail(PTB_E_NOMEM, "ptb_bvh_build_host: out of memory");
-    std::memcpy(*nodes, width == 4 ? (const void*)b.nodes4.data() : (const void*)b.nodes.data(), node_bytes);
+    std::memcpy(*nodes, width == 1 ? (const void*)b.flat.data() : width == 4 ? (const void*)b.nodes4.data() : (const void*)b.nodes.data(), node_bytes);
     std::memcpy(*tri_order, b.tri_order.data(), b.tri_order.size() * sizeof(int32_t));
     if (ordered_tris) {
         *ordered_tris = static_cast<ptb_bvh_tri*>(std::malloc(b.tris.size() * sizeof(ptb_bvh_tri)));
         if (!*ordered_tris) return fail(PTB_E_NOMEM, "ptb_bvh_build_host: out of memory");
         std::memcpy(*ordered_tris, b.tris.data(), b.tris.size() * sizeof(ptb_bvh_tri));
     }
-    *n_nodes = int(width == 4 ? b.nodes4.size() : b.nodes.size());
-    if (depth) *depth = width == 4 ? b.depth4 : b.depth;
-    if (smem_nodes) *smem_nodes = width == 4 ? b.smem_nodes4 : b.smem_nodes;
+    *n_nodes = int(width == 1 ? b.flat.size() : width == 4 ? b.nodes4.size() : b.nodes.size());
+    if (depth) *depth = width == 1 ? 1 : width == 4 ? b.depth4 : b.depth;
+    if (smem_nodes) *smem_nodes = width == 1 ? int(b.flat.size()) : width == 4 ? b.smem_nodes4 : b.smem_nodes;
     return PTB_OK;
 }
 
@@ -503,6 +520,11 @@ extern "C" int ptb_scene_info(ptb_scene* s, int* n_nodes, int* n_tris, int* dept
 }
 
 extern "C" int ptb_scene_bvh_width(ptb_scene* s) { return s ? s->width : 0; }
+extern "C" int ptb_scene_mode_width(ptb_scene* s, int mode) {
+    if (!s) return 0;
+    const int c = mode_class(s, mode);
+    return c == ptd::PTD_FLAT ? 1 : c == ptd::PTD_SMALL4 ? 4 : 2;
+}
 
 extern "C" int ptb_scene_copy_bvh(ptb_scene* s, void* nodes, int32_t* tri_order) {
     if (!s) return fail(PTB_E_INVALID, "ptb_scene_copy_bvh: null scene");
@@ -516,26 +538,48 @@ extern "C" int ptb_scene_copy_bvh(ptb_scene* s, void* nodes, int32_t* tri_order)
         s->host_copy_valid = true;
     }
     if (nodes) {
-        if (s->width == 4) std::memcpy(nodes, s->bvh.nodes4.data(), s->bvh.nodes4.size() * sizeof(ptb_bvh_node4));
+        if (s->width == 1) std::memcpy(nodes, s->bvh.flat.data(), s->bvh.flat.size() * sizeof(ptb_bvh_leafbox));
+        else if (s->width == 4) std::memcpy(nodes, s->bvh.nodes4.data(), s->bvh.nodes4.size() * sizeof(ptb_bvh_node4));
         else std::memcpy(nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptb_bvh_node));
     }
     if (tri_order) std::memcpy(tri_order, s->bvh.tri_order.data(), s->bvh.tri_order.size() * sizeof(int32_t));
     return PTB_OK;
 }
 
-static ptd::SceneDev scene_dev(const ptb_scene* s) {
+// Which form a render mode uses.  A FLAT scene tests every leaf box for every ray: that beats the tree walk when the rays of
+// a warp go different ways (PATH: C4 +26 %, AO: +5 %), but coherent rays walk the 4-wide tree in lock-step at no loss and
+// touch fewer boxes (DIRECT, primary + one shadow ray towards the light: the tree is 7 % faster).  Measured on B200,
+// profiles/ (round 2).  The scene keeps both forms resident; results are identical, the visit statistics follow the form.
+static int mode_class(const ptb_scene* s, int mode) {
+    if (s->cls == ptd::PTD_FLAT && s->d_nodes4 && mode == PTB_MODE_DIRECT) return ptd::PTD_SMALL4;
+    return s->cls;
+}
+
+static ptd::SceneDev scene_dev(const ptb_scene* s, int cls) {
     ptd::SceneDev d;
     d.nodes = s->d_nodes; d.tris = s->d_tris; d.tris_orig = s->d_tris_orig; d.mats = s->d_mats;
     d.n_nodes = s->n_nodes; d.n_tris = s->n_tris; d.n_mats = s->n_mats;
+    if (cls == ptd::PTD_SMALL4 && s->cls == ptd::PTD_FLAT) {  // the resident 4-wide tree of a FLAT scene
+        d.nodes = s->d_nodes4; d.n_nodes = int(s->bvh.nodes4.size());
+        d.smem_nodes = s->bvh.smem_nodes4; d.small = 1; d.flat_n = 0; d.lstack = 0; d.ld256 = 0;
+        d.stack_depth = 3 * s->bvh.depth4 + 1;
+        return d;
+    }
     // Large scenes stage only the top of the tree: a 64-node (4 KB) prefix keeps >= 6 CTAs per SM
     // resident (measured on the 2M-triangle scene: 1024 nodes 0.83, 256 nodes 1.81, 64 nodes 2.28 Grays/s).
     const int cap = s->dev->tune[4] > 0 ? s->dev->tune[4] : 64;
     d.smem_nodes = s->small ? s->bfs_nodes : (s->bfs_nodes < cap ? s->bfs_nodes : cap);
     d.small = s->small ? 1 : 0;
+    d.flat_n = 0;
+    if (s->cls == ptd::PTD_FLAT) {
+        d.flat_n = (int(s->bvh.flat.size()) + 1) & ~1;
+        d.smem_nodes = 0;
+    }
     d.stack_depth = s->width == 4 ? 3 * s->depth + 1 : s->depth + 1;  // a 4-wide visit defers up to three children
     // scenes traversed from L2/HBM keep the stack in local memory: shared memory then holds only the node
     // prefix and occupancy is bounded by registers (C5: +2.4 %); tune[2]=2 forces the shared-memory stack
     d.lstack = (!s->small && s->dev->tune[2] != 2 && s->depth + 1 <= PTD_LSTACK_ENTRIES) ? 1 : 0;
+    d.ld256 = s->dev->tune[8] == 1 ? 0 : 1;  // tune[8]=1: fetch global nodes with four 128-bit loads instead of two 256-bit ones
     return d;
 }
 
@@ -559,7 +603,7 @@ static int set_smem(K kernel, size_t smem, int block, int* per_sm = nullptr) {
     return PTB_OK;
 }
 
-template <int MODE, bool BVH, bool SMALL, bool STATS>
+template <int MODE, bool BVH, int SMALL, bool STATS>
 static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::RenderArgs& a) {
     const int block = (a.tune[3] == 64 || a.tune[3] == 32) ? a.tune[3] : 128;
     if (MODE == PTB_MODE_PATH && a.tune[5] == 0) {  // persistent grid with path regeneration (tune[5]=1: one sample per thread)
@@ -588,15 +632,18 @@ static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::Re
 }
 
 template <int MODE>
-static int launch_mega_m(ptb_device* dev, const ptd::SceneDev& sc, const ptd::RenderArgs& a, bool bvh, bool small, bool stats) {
+static int launch_mega_m(ptb_device* dev, const ptd::SceneDev& sc, const ptd::RenderArgs& a, bool bvh, int small, bool stats) {
+    using namespace ptd;
+    if (!bvh && small == PTD_FLAT) small = PTD_SMALL4;  // brute force only needs the staged triangles
 #define PTB_CASE(B, S, T) if (bvh == B && small == S && stats == T) return launch_mega_t<MODE, B, S, T>(dev, sc, a)
-    PTB_CASE(true, true, false); PTB_CASE(true, true, true); PTB_CASE(true, false, false); PTB_CASE(true, false, true);
-    PTB_CASE(false, true, false); PTB_CASE(false, true, true); PTB_CASE(false, false, false); PTB_CASE(false, false, true);
+    PTB_CASE(true, PTD_FLAT, false); PTB_CASE(true, PTD_FLAT, true);
+    PTB_CASE(true, PTD_SMALL4, false); PTB_CASE(true, PTD_SMALL4, true); PTB_CASE(true, PTD_LARGE, false); PTB_CASE(true, PTD_LARGE, true);
+    PTB_CASE(false, PTD_SMALL4, false); PTB_CASE(false, PTD_SMALL4, true); PTB_CASE(false, PTD_LARGE, false); PTB_CASE(false, PTD_LARGE, true);
 #undef PTB_CASE
     return fail(PTB_E_INVALID, "launch_mega: unreachable");
 }
 
-static int launch_mega(ptb_device* dev, int mode, const ptd::SceneDev& sc, const ptd::RenderArgs& a, bool bvh, bool small, bool stats) {
+static int launch_mega(ptb_device* dev, int mode, const ptd::SceneDev& sc, const ptd::RenderArgs& a, bool bvh, int small, bool stats) {
     switch (mode) {
         case PTB_MODE_PRIMARY: return launch_mega_m<PTB_MODE_PRIMARY>(dev, sc, a, bvh, small, stats);
         case PTB_MODE_AO: return launch_mega_m<PTB_MODE_AO>(dev, sc, a, bvh, small, stats);
@@ -670,10 +717,10 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
     if (p->mode == PTB_MODE_DIRECT && (p->light_quad < 0 || p->light_quad >= scene->n_mats))
         return fail(PTB_E_INVALID, "ptb_render: light_quad %d out of range", p->light_quad);
 
-    ptd::SceneDev sc = scene_dev(scene);
+    const int small = mode_class(scene, p->mode);
+    ptd::SceneDev sc = scene_dev(scene, small);
     const bool bvh = p->accel == PTB_ACCEL_BVH;
     const bool stats = p->collect_stats != 0;
-    const bool small = scene->small;
 
     // batch of frames kept in flight
     int fpb = p->frames_per_batch;
@@ -718,7 +765,7 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
     a.stats = stats ? d_stats : nullptr;
     a.stats_frame = p->first_frame + p->n_frames - 1;
     a.counters = dev->counters;
-    for (int k = 0; k < 8; ++k) a.tune[k] = dev->tune[k];
+    for (int k = 0; k < 16; ++k) a.tune[k] = dev->tune[k];
 
     // AUTO = the faster integrator as measured on B200.  With 4-wide nodes for
     // shared-memory-resident scenes and path regeneration, the megakernel wins every BASELINE configuration
@@ -1243,7 +1290,7 @@ extern "C" int ptb_launch_deserialize(ptb_device* dev, const char* path, ptb_buf
 // ---- measurement hooks -----------------------------------------------------------------------------------------
 
 extern "C" int ptb_device_set_tuning(ptb_device* dev, int index, int value) {
-    if (!dev || index < 0 || index >= 8) return fail(PTB_E_INVALID, "ptb_device_set_tuning: bad arguments");
+    if (!dev || index < 0 || index >= 16) return fail(PTB_E_INVALID, "ptb_device_set_tuning: bad arguments");
     dev->tune[index] = value;
     return PTB_OK;
 }
@@ -1303,9 +1350,10 @@ extern "C" int ptb_trace(ptb_device* dev, ptb_scene* scene, int accel, int any_h
     CU_TRY(cudaMemcpyAsync(d_o.p, o, 12 * n, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_d.p, d, 12 * n, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_tm.p, tmax, 4 * n, cudaMemcpyHostToDevice, st));
-    ptd::SceneDev sc = scene_dev(scene);
+    ptd::SceneDev sc = scene_dev(scene, scene->cls);
     ptd::TraceArgs a{n_rays, d_o.p, d_d.p, d_tm.p, d_tri.p, d_t.p, d_u.p, d_v.p, d_vis.p, d_tst.p};
-    const bool bvh = accel == PTB_ACCEL_BVH, small = scene->small, any = any_hit != 0;
+    const bool bvh = accel == PTB_ACCEL_BVH, any = any_hit != 0;
+    const int small = (!bvh && scene->cls == ptd::PTD_FLAT) ? ptd::PTD_SMALL4 : scene->cls;
     const int block = 128;
     const unsigned grid = (unsigned)((n + block - 1) / block);
     const size_t smem = ptd::scene_smem_bytes(sc, bvh, small, block);
@@ -1315,8 +1363,9 @@ extern "C" int ptb_trace(ptb_device* dev, ptb_scene* scene, int accel, int any_h
         if ((rc = set_smem(k, smem, block))) return rc;                               \
         k<<<grid, block, smem, st>>>(sc, a);                                   \
     }
-    PTB_TRACE_CASE(true, true, true) PTB_TRACE_CASE(true, true, false) PTB_TRACE_CASE(true, false, true) PTB_TRACE_CASE(true, false, false)
-    PTB_TRACE_CASE(false, true, true) PTB_TRACE_CASE(false, true, false) PTB_TRACE_CASE(false, false, true) PTB_TRACE_CASE(false, false, false)
+    PTB_TRACE_CASE(true, true, 2) PTB_TRACE_CASE(true, false, 2)
+    PTB_TRACE_CASE(true, true, 1) PTB_TRACE_CASE(true, true, 0) PTB_TRACE_CASE(true, false, 1) PTB_TRACE_CASE(true, false, 0)
+    PTB_TRACE_CASE(false, true, 1) PTB_TRACE_CASE(false, true, 0) PTB_TRACE_CASE(false, false, 1) PTB_TRACE_CASE(false, false, 0)
 #undef PTB_TRACE_CASE
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(out_tri, d_tri.p, 4 * n, cudaMemcpyDeviceToHost, st));

@@ -15,6 +15,7 @@ struct BuiltBvh {
     std::vector<ptb_bvh_node> nodes;   // binary tree; [0] is the root; first `smem_nodes` in BFS order
     std::vector<ptb_bvh_node4> nodes4; // the same tree collapsed to 4-wide nodes (only for scenes of <= 2048 triangles)
     int depth4 = 0, smem_nodes4 = 0;
+    std::vector<ptb_bvh_leafbox> flat; // the leaf slots in leaf order (only for scenes of <= 32 leaves and <= 64 triangles)
     std::vector<ptb_bvh_tri> tris;     // BVH order, precomputed-edge layout
     std::vector<int32_t> tri_order;    // BVH position -> caller's triangle index
     int depth = 0;                     // longest root-to-leaf chain of internal nodes

@@ -36,13 +36,14 @@ PTD_FI void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* mbar) {
 
 // NODES: stage the node prefix and carve the traversal stack; TRIS_BVH: triangle
 // positions refer to the BVH-ordered array (else the caller-ordered one).
-template <bool NODES, bool SMALL, bool TRIS_BVH = NODES>
+template <bool NODES, int SMALL, bool TRIS_BVH = NODES>
 PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
     constexpr bool BVH = NODES;
+    constexpr bool STACK = NODES && SMALL != PTD_FLAT;  // FLAT scenes need no traversal stack
     Ctx c;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
     unsigned char* p = smem + 16;
-    const uint32_t node_bytes = BVH ? (uint32_t)sc.smem_nodes * (SMALL ? 128u : 64u) : 0u;
+    const uint32_t node_bytes = !BVH ? 0u : SMALL == PTD_FLAT ? (uint32_t)sc.flat_n * 32u : (uint32_t)sc.smem_nodes * (SMALL ? 128u : 64u);
     const uint32_t tri_bytes = SMALL ? (uint32_t)sc.n_tris * 48u : 0u;
     const uint32_t mat_bytes = SMALL ? (uint32_t)sc.n_mats * 32u : 0u;
     float4* s_nodes = reinterpret_cast<float4*>(p);
@@ -85,7 +86,7 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
     c.g_tris = TRIS_BVH ? sc.tris : sc.tris_orig;
     c.g_mats = sc.mats;
     c.stride_bytes = blockDim.x * 4u;
-    const uint32_t stack_bytes = (NODES && !sc.lstack) ? (uint32_t)sc.stack_depth * blockDim.x * 4u : 0u;
+    const uint32_t stack_bytes = (STACK && !sc.lstack) ? (uint32_t)sc.stack_depth * blockDim.x * 4u : 0u;
     // two disjoint areas: warps of one CTA can be in a closest-hit and an any-hit query at the same time (AO, DIRECT)
     c.s_stack64 = smem_u32(s_stack) + threadIdx.x * 8u;                       // (ref, entry distance) pairs
     c.s_stack_ref = smem_u32(s_stack) + 2u * stack_bytes + threadIdx.x * 4u;  // any-hit: references only
@@ -93,15 +94,17 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
     c.smem_nodes = sc.smem_nodes;
     c.n_tris = sc.n_tris;
     c.lstack = nullptr;
+    c.ld256 = sc.ld256;
+    c.flat_n = sc.flat_n;
     return c;
 }
 
 // host helper: bytes of dynamic shared memory for a launch
-static inline size_t scene_smem_bytes(const SceneDev& sc, bool bvh, bool small, int block, size_t scratch_per_thread = 0) {
+static inline size_t scene_smem_bytes(const SceneDev& sc, bool bvh, int small, int block, size_t scratch_per_thread = 0) {
     size_t b = 16;
-    if (bvh) b += (size_t)sc.smem_nodes * (small ? 128 : 64);
+    if (bvh) b += small == PTD_FLAT ? (size_t)sc.flat_n * 32 : (size_t)sc.smem_nodes * (small ? 128 : 64);
     if (small) b += (size_t)sc.n_tris * 48 + (size_t)sc.n_mats * 32;
-    if (bvh && !sc.lstack) b += (size_t)sc.stack_depth * block * 12;  // closest-hit pairs (8 B) + any-hit references (4 B)
+    if (bvh && small != PTD_FLAT && !sc.lstack) b += (size_t)sc.stack_depth * block * 12;  // closest-hit pairs (8 B) + any-hit references (4 B)
     return b + scratch_per_thread * block;
 }
 
@@ -123,7 +126,7 @@ struct RenderArgs {
     ptb_pixel_stats* stats;     // per local pixel, written for stats_frame only
     int stats_frame;
     unsigned long long* counters;
-    int tune[8];           // experiment knobs (ptb_device_set_tuning); never change results
+    int tune[16];          // experiment knobs (ptb_device_set_tuning); never change results
 };
 
 template <bool STATS>
@@ -157,7 +160,7 @@ struct RayCount {
 
 // One iteration of the path loop, GenerateColors.cl:229-258.  Returns true when the path goes on
 // (r, mask, seed updated), false when it ended; radiance accumulates either way.
-template <bool BVH, bool SMALL, bool STATS>
+template <bool BVH, int SMALL, bool STATS>
 PTD_FI bool path_segment(const Ctx& c, Ray& r, uint32_t& seed, V3& radiance, V3& mask, int i, int max_depth,
                          SampleStats<STATS>& st, RayCount& rc, QueryStats& qs) {
     Hit h;
@@ -195,7 +198,7 @@ PTD_FI bool path_segment(const Ctx& c, Ray& r, uint32_t& seed, V3& radiance, V3&
 }
 
 // GenerateColors.cl:223-261 with BOUNCES -> max_depth
-template <bool BVH, bool SMALL, bool STATS>
+template <bool BVH, int SMALL, bool STATS>
 PTD_FI V3 trace_rays(const Ctx& c, Ray r, uint32_t& seed, int max_depth, SampleStats<STATS>& st, RayCount& rc,
                      QueryStats& qs) {
     V3 radiance = mk(0.0f, 0.0f, 0.0f);  // :225
@@ -206,7 +209,7 @@ PTD_FI V3 trace_rays(const Ctx& c, Ray r, uint32_t& seed, int max_depth, SampleS
 }
 
 // BUILD-DEFINED C1
-template <bool BVH, bool SMALL, bool STATS>
+template <bool BVH, int SMALL, bool STATS>
 PTD_FI V3 sample_primary(const Ctx& c, Ray r, SampleStats<STATS>& st, RayCount& rc, QueryStats& qs) {
     Hit h;
     const bool hit = q_closest<BVH, SMALL, STATS>(c, r.o, r.d, h, qs);
@@ -222,7 +225,7 @@ PTD_FI V3 sample_primary(const Ctx& c, Ray r, SampleStats<STATS>& st, RayCount& 
 }
 
 // BUILD-DEFINED C2
-template <bool BVH, bool SMALL, bool STATS>
+template <bool BVH, int SMALL, bool STATS>
 PTD_FI V3 sample_ao(const Ctx& c, Ray r, uint32_t& seed, int ns, float max_dist, SampleStats<STATS>& st,
                     RayCount& rc, QueryStats& qs) {
     Hit h;
@@ -253,7 +256,7 @@ PTD_FI V3 sample_ao(const Ctx& c, Ray r, uint32_t& seed, int ns, float max_dist,
 }
 
 // BUILD-DEFINED C3
-template <bool BVH, bool SMALL, bool STATS>
+template <bool BVH, int SMALL, bool STATS>
 PTD_FI V3 sample_direct(const Ctx& c, const RenderArgs& a, Ray r, uint32_t& seed, SampleStats<STATS>& st,
                         RayCount& rc, QueryStats& qs) {
     Hit h;
@@ -314,7 +317,7 @@ PTD_FI V3 sample_direct(const Ctx& c, const RenderArgs& a, Ray r, uint32_t& seed
 
 // ---- megakernel: one thread per sample ---------------------------------------------------------
 
-template <int MODE, bool BVH, bool SMALL, bool STATS>
+template <int MODE, bool BVH, int SMALL, bool STATS>
 __global__ void __launch_bounds__(128, ((MODE == PTB_MODE_AO || MODE == PTB_MODE_DIRECT) && BVH && SMALL) ? 8 : 0) k_mega(const SceneDev sc, const RenderArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Ctx c = stage_scene<BVH, SMALL>(sc, smem);
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(128, ((MODE == PTB_MODE_AO || MODE == PTB_MODE
 // on average).  Here the grid is persistent and a lane whose path ended immediately draws the next sample
 // slot from a global counter (one warp-aggregated atomicAdd per refill), so every warp iteration is one
 // path segment for (nearly) 32 live lanes.  Per-sample arithmetic is unchanged -> identical results.
-template <bool BVH, bool SMALL, bool STATS>
+template <bool BVH, int SMALL, bool STATS>
 __global__ void __launch_bounds__(128) k_mega_path_regen(const SceneDev sc, const RenderArgs a,
                                                          unsigned long long* work_counter) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -549,7 +552,7 @@ struct TraceArgs {
     uint32_t* out_tests;
 };
 
-template <bool BVH, bool ANY, bool SMALL>
+template <bool BVH, bool ANY, int SMALL>
 __global__ void __launch_bounds__(128) k_trace(const SceneDev sc, const TraceArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Ctx c = stage_scene<BVH, SMALL>(sc, smem);

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) wf_generate(const RenderArgs a, const WfB
 }
 
 // ---- extend --------------------------------------------------------------------------------------
-template <bool BVH, bool SMALL, bool STATS>
+template <bool BVH, int SMALL, bool STATS>
 __global__ void __launch_bounds__(128) wf_extend(const SceneDev sc, const WfBuffers w, const int depth, const int qi,
                                                  unsigned long long* counters) {
     const unsigned int n = w.counts[depth];
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) wf_extend(const SceneDev sc, const WfBuff
 // runs: internal nodes until no lane has one, then the leaves.  Per-ray traversal (order, visit counts,
 // results) is exactly bvh_query's; only which lanes run together changes.
 //   IO::load(i, o, d, tmax) -> false for a hole;  IO::store(i, hit, h, qs) publishes one ray's result.
-template <bool ANY, bool SMALL, bool STATS, class IO>
+template <bool ANY, int SMALL, bool STATS, class IO>
 PTD_FI void trace_persistent(const Ctx& c, IO& io, const unsigned int n_rays, unsigned int* work_counter,
                              const int refill_thr, uint32_t& n_traced, QueryStats& total) {
     const unsigned lane = threadIdx.x & 31u;
@@ -209,7 +209,7 @@ struct ExtendIO {
     }
 };
 
-template <bool SMALL, bool STATS>
+template <int SMALL, bool STATS>
 struct ExtendStore : ExtendIO {
     const Ctx* c;
     PTD_FI void store(unsigned int i, bool hit_any, const Hit& h, const QueryStats& qs) {
@@ -235,7 +235,7 @@ struct ExtendStore : ExtendIO {
     }
 };
 
-template <bool SMALL, bool STATS>
+template <int SMALL, bool STATS>
 __global__ void __launch_bounds__(128) wf_extend_p(const SceneDev sc, const WfBuffers w, const int depth, const int qi,
                                                    unsigned long long* counters, const int refill_thr) {
     const unsigned int n = w.counts[depth];
@@ -303,7 +303,7 @@ struct ShadowIO {
     }
 };
 
-template <int MODE, bool SMALL, bool STATS>
+template <int MODE, int SMALL, bool STATS>
 __global__ void __launch_bounds__(128) wf_shadow_p(const SceneDev sc, const RenderArgs a, const WfBuffers w,
                                                    const unsigned int n_rays, unsigned int* work,
                                                    unsigned long long* counters, const int refill_thr) {
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(128) wf_shadow_p(const SceneDev sc, const Rend
 }
 
 // ---- shade: full path (GenerateColors.cl:233-257) ---------------------------------------------------
-template <bool BVH, bool SMALL, bool STATS>
+template <bool BVH, int SMALL, bool STATS>
 __global__ void __launch_bounds__(128) wf_shade_path(const SceneDev sc, const RenderArgs a, const WfBuffers w,
                                                      const int depth, const int qi) {
     const unsigned int n = w.counts[depth];
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(128) wf_shade_path(const SceneDev sc, const Re
 }
 
 // ---- shade: primary / AO / direct -------------------------------------------------------------------
-template <int MODE, bool BVH, bool SMALL, bool STATS>
+template <int MODE, bool BVH, int SMALL, bool STATS>
 __global__ void __launch_bounds__(128) wf_shade_first(const SceneDev sc, const RenderArgs a, const WfBuffers w) {
     const unsigned int n = w.counts[0];
     if (blockIdx.x * blockDim.x >= n) return;
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(128) wf_shade_first(const SceneDev sc, const R
 }
 
 // ---- shadow / AO any-hit stage -----------------------------------------------------------------------
-template <int MODE, bool BVH, bool SMALL, bool STATS>
+template <int MODE, bool BVH, int SMALL, bool STATS>
 __global__ void __launch_bounds__(128) wf_shadow(const SceneDev sc, const RenderArgs a, const WfBuffers w,
                                                  const long long n_rays, unsigned long long* counters) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -623,13 +623,14 @@ static int wf_smem(K kernel, size_t smem) {
     return 0;
 }
 
-template <bool BVH, bool SMALL, bool STATS>
+template <bool BVH, int SMALL, bool STATS>
 static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArgs& a, const WfBuffers& w,
                   unsigned long long* counters, uint64_t* launches, int sm_count) {
     const long long P = (long long)a.frames_in_batch * a.n_local;
     const int block = 128;
     const unsigned grid = (unsigned)((P + block - 1) / block);
-    const bool persist = BVH && a.tune[6] == 0;            // tune[6]=1: one thread per ray (no dynamic fetch)
+    // tune[6]=1: one thread per ray (no dynamic fetch).  FLAT scenes have no node loop to keep busy: one thread per ray.
+    const bool persist = BVH && SMALL != PTD_FLAT && a.tune[6] == 0;
     const int refill_thr = a.tune[7] > 0 ? a.tune[7] : 8;  // idle lanes that trigger a refill
     auto pgrid = [&](auto kernel, size_t smem, long long n_items) -> unsigned {
         int per_sm = 0;
@@ -649,7 +650,7 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
     if (mode == PTB_MODE_PATH) {
         auto shade = wf_shade_path<BVH, SMALL, STATS>;
         if ((rc = wf_smem(shade, smem_s))) return rc;
-        auto extp = wf_extend_p<SMALL, STATS>;
+        auto extp = wf_extend_p<SMALL == PTD_FLAT ? PTD_SMALL4 : SMALL, STATS>;  // never launched for FLAT scenes
         if (persist && (rc = wf_smem(extp, smem_q))) return rc;
         const unsigned pg = persist ? pgrid(extp, smem_q, P) : 0u;
         for (int depth = 0; depth < a.max_depth; ++depth) {
@@ -662,7 +663,7 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
         WF_TRY(cudaGetLastError());
     } else {
         if (persist) {
-            auto extp = wf_extend_p<SMALL, STATS>;
+            auto extp = wf_extend_p<SMALL == PTD_FLAT ? PTD_SMALL4 : SMALL, STATS>;
             if ((rc = wf_smem(extp, smem_q))) return rc;
             extp<<<pgrid(extp, smem_q, P), block, smem_q, st>>>(sc, w, 0, 0, counters, refill_thr);
         } else {
@@ -680,7 +681,7 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
             k<<<grid, block, smem_s, st>>>(sc, a, w);
             const long long nr = P * a.ao_samples;
             if (persist) {
-                auto shp = wf_shadow_p<PTB_MODE_AO, SMALL, STATS>;
+                auto shp = wf_shadow_p<PTB_MODE_AO, SMALL == PTD_FLAT ? PTD_SMALL4 : SMALL, STATS>;
                 if ((rc = wf_smem(shp, smem_q))) return rc;
                 shp<<<pgrid(shp, smem_q, nr), block, smem_q, st>>>(sc, a, w, (unsigned int)nr, w.work + 1, counters, refill_thr);
             } else {
@@ -694,7 +695,7 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
             if ((rc = wf_smem(k, smem_s))) return rc;
             k<<<grid, block, smem_s, st>>>(sc, a, w);
             if (persist) {
-                auto shp = wf_shadow_p<PTB_MODE_DIRECT, SMALL, STATS>;
+                auto shp = wf_shadow_p<PTB_MODE_DIRECT, SMALL == PTD_FLAT ? PTD_SMALL4 : SMALL, STATS>;
                 if ((rc = wf_smem(shp, smem_q))) return rc;
                 shp<<<pgrid(shp, smem_q, P), block, smem_q, st>>>(sc, a, w, (unsigned int)P, w.work + 1, counters, refill_thr);
             } else {
@@ -715,7 +716,7 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
 
 // scratch layout for one batch; (re)allocates *scratch when it is too small
 static int wavefront_render(cudaStream_t st, void** scratch, size_t* scratch_bytes, unsigned long long* counters,
-                            int mode, const SceneDev& sc, const RenderArgs& a, bool bvh, bool small, bool stats,
+                            int mode, const SceneDev& sc, const RenderArgs& a, bool bvh, int small, bool stats,
                             int sm_count, uint64_t* launches) {
     const size_t P = (size_t)a.frames_in_batch * a.n_local;
     const size_t n_shadow = mode == PTB_MODE_AO ? P * (size_t)a.ao_samples : (mode == PTB_MODE_DIRECT ? P : 0);
@@ -758,8 +759,10 @@ static int wavefront_render(cudaStream_t st, void** scratch, size_t* scratch_byt
     if (P * (mode == PTB_MODE_AO ? (size_t)a.ao_samples : 1) >= 0xffffffffull)
         return ptb::fail(PTB_E_INVALID, "wavefront_render: batch too large for 32-bit ray indices; lower frames_per_batch");
 #define WF_CASE(B, S, T) if (bvh == B && small == S && stats == T) return wf_run<B, S, T>(st, mode, sc, a, w, counters, launches, sm_count)
-    WF_CASE(true, true, false); WF_CASE(true, true, true); WF_CASE(true, false, false); WF_CASE(true, false, true);
-    WF_CASE(false, true, false); WF_CASE(false, true, true); WF_CASE(false, false, false); WF_CASE(false, false, true);
+    if (!bvh && small == PTD_FLAT) small = PTD_SMALL4;  // brute force only needs the staged triangles
+    WF_CASE(true, PTD_FLAT, false); WF_CASE(true, PTD_FLAT, true);
+    WF_CASE(true, PTD_SMALL4, false); WF_CASE(true, PTD_SMALL4, true); WF_CASE(true, PTD_LARGE, false); WF_CASE(true, PTD_LARGE, true);
+    WF_CASE(false, PTD_SMALL4, false); WF_CASE(false, PTD_SMALL4, true); WF_CASE(false, PTD_LARGE, false); WF_CASE(false, PTD_LARGE, true);
 #undef WF_CASE
     return ptb::fail(PTB_E_INVALID, "wavefront_render: unreachable");
 }

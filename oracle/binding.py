@@ -38,6 +38,9 @@ NODE4_DTYPE = np.dtype(  # 4-wide node, 128 bytes (ptb_bvh_node4)
         ("c3", "<f4", 3), ("pad2", "<i4"), ("e3", "<f4", 3), ("pad3", "<i4"),
     ]
 )
+LEAFBOX_DTYPE = np.dtype(  # flat form, 32 bytes (ptb_bvh_leafbox)
+    [("c", "<f4", 3), ("mask_lo", "<u4"), ("e", "<f4", 3), ("mask_hi", "<u4")]
+)
 STATS_DTYPE = np.dtype(
     [
         ("tri", "<i4"), ("quad", "<i4"), ("t_bits", "<u4"), ("visits_primary", "<u4"),
@@ -53,6 +56,11 @@ class Bvh(C.Structure):
         ("nodes", C.c_void_p), ("n_nodes", C.c_int32),
         ("tri_order", C.c_void_p), ("n_tris", C.c_int32), ("width", C.c_int32),
     ]
+
+
+class BvhParams(C.Structure):
+    _fields_ = [("max_leaf", C.c_int32), ("pad_rel", C.c_float), ("n_bins", C.c_int32), ("smem_nodes", C.c_int32),
+                ("traverse_cost", C.c_float)]
 
 
 class Params(C.Structure):
@@ -104,6 +112,8 @@ def lib():
         L.ora_tessellate.restype = C.c_int
         L.ora_max_threads.restype = C.c_int
         L.ora_local_pixel_count.restype = C.c_int
+        L.ora_bvh_build.restype = C.c_int
+        L.ora_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -168,9 +178,53 @@ def make_bvh(nodes, tri_order):
     """nodes: NODE_DTYPE (binary) or NODE4_DTYPE (4-wide) array; tri_order: int32 array.  Returns (Bvh, keepalive)."""
     nodes = np.ascontiguousarray(nodes)
     order = np.ascontiguousarray(tri_order, np.int32)
-    width = {64: 2, 128: 4}[nodes.dtype.itemsize]
+    width = {64: 2, 128: 4, 32: 1}[nodes.dtype.itemsize]
     b = Bvh(nodes.ctypes.data, len(nodes), order.ctypes.data, len(order), width)
     return b, (nodes, order)
+
+
+def bvh_params(**kw):
+    p = BvhParams()
+    lib().ora_bvh_params_default(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def build_bvh(tris, params=None, width=None):
+    """The oracle's own builder (oracle_bvh.c).  width None = the scene-class rule of the product: FLAT (1) for <= 64
+    triangles in <= 32 leaves, else 4-wide when the 4-wide nodes + triangles + materials of the scene fit 32 KB of
+    shared memory, else binary.
+    Returns {"nodes", "tri_order", "depth", "bfs_nodes", "width"}."""
+    tris = np.ascontiguousarray(tris)
+
+    def one(w):
+        nodes_p, order_p = C.c_void_p(), C.c_void_p()
+        nn, depth, bfs = C.c_int(0), C.c_int(0), C.c_int(0)
+        rc = lib().ora_bvh_build(_p(tris), len(tris), C.byref(params) if params is not None else None, w, C.byref(nodes_p),
+                                 C.byref(nn), C.byref(order_p), C.byref(depth), C.byref(bfs))
+        if rc != 0:
+            raise RuntimeError(f"ora_bvh_build(width={w}) -> {rc}")
+        dt = {4: NODE4_DTYPE, 2: NODE_DTYPE, 1: LEAFBOX_DTYPE}[w]
+        nodes = np.frombuffer(C.string_at(nodes_p, nn.value * dt.itemsize), dt).copy()
+        order = np.frombuffer(C.string_at(order_p, len(tris) * 4), np.int32).copy()
+        lib().ora_free(nodes_p)
+        lib().ora_free(order_p)
+        return {"nodes": nodes, "tri_order": order, "depth": depth.value, "bfs_nodes": bfs.value, "width": w}
+
+    if width is not None:
+        return one(width)
+    if len(tris) <= 64:
+        try:
+            return one(1)
+        except RuntimeError:
+            pass  # more than 32 leaves
+    if len(tris) <= 2048:
+        b4 = one(4)
+        n_mats = int(tris["id"].max()) + 1
+        if len(b4["nodes"]) * 128 + len(tris) * 48 + n_mats * 32 <= 32 * 1024 and b4["bfs_nodes"] == len(b4["nodes"]):
+            return b4
+    return one(2)
 
 
 def trace(tris, o, d, tmax, bvh=None, any_hit=False):

@@ -590,8 +590,57 @@ static int bvh_query2(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, 
     }
 }
 
+/* FLAT form (scenes of <= 32 leaves and <= 64 triangles; BUILD-DEFINED, the specification of the product's flat query):
+ *  phase A: slab-test EVERY leaf box against [0, tmax] (tmax = 1e20 for closest-hit) in record order; the leaves that
+ *           pass contribute their triangle masks; visits = number of leaves that passed;
+ *  phase B: test the selected triangles in ascending position of the ordered array.  Closest: accept when t < best_t, or
+ *           t == best_t and the triangle's caller index is lower (== the reference's "first index wins"); no leaf is
+ *           culled by best_t.  Any: return at the first triangle with 0 < t < tmax.                                   */
+static int bvh_query_flat(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, float tmax, int any_hit, qhit* h,
+                          uint32_t* visits, qctr* c) {
+    float invd[3] = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
+    float ood[3] = {o.x * invd[0], o.y * invd[1], o.z * invd[2]};
+    const ora_bvh_leafbox* lb = (const ora_bvh_leafbox*)bvh->nodes;
+    uint64_t tm = 0;
+    if (any_hit) c->any++; else c->closest++;
+    for (int k = 0; k < bvh->n_nodes; k++) {
+        float tn;
+        if (bvh_slab(lb[k].c, lb[k].e, invd, ood, tmax, &tn)) {
+            tm |= (uint64_t)lb[k].mask_lo | ((uint64_t)lb[k].mask_hi << 32);
+            (*visits)++;
+            c->nodes++;
+        }
+    }
+    float best_t = tmax, best_u = 0, best_v = 0;
+    int best_tri = -1;
+    while (tm) {
+        const int pos = __builtin_ctzll(tm);
+        tm &= tm - 1;
+        const int idx = bvh->tri_order[pos];
+        float t, u, v;
+        if (!mt_core(o, d, &tris[idx], &t, &u, &v, c)) continue;
+        if (any_hit) {
+            if (t < best_t) {
+                c->acc++;
+                h->t = t; h->u = u; h->v = v; h->tri = idx;
+                return 1;
+            }
+        } else if (t < best_t || (t == best_t && best_tri >= 0 && idx < best_tri)) {
+            c->acc++;
+            best_t = t; best_u = u; best_v = v; best_tri = idx;
+        }
+    }
+    if (best_tri >= 0 && !any_hit) {
+        h->t = best_t; h->u = best_u; h->v = best_v; h->tri = best_tri;
+        return 1;
+    }
+    h->tri = -1;
+    return 0;
+}
+
 static int bvh_query(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, float tmax, int any_hit, qhit* h,
                      uint32_t* visits, qctr* c) {
+    if (bvh->width == 1) return bvh_query_flat(tris, bvh, o, d, tmax, any_hit, h, visits, c);
     if (bvh->width == 4) return bvh_query4(tris, bvh, o, d, tmax, any_hit, h, visits, c);
     return bvh_query2(tris, bvh, o, d, tmax, any_hit, h, visits, c);
 }

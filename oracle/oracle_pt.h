@@ -58,9 +58,9 @@ typedef struct ora_triangle {
     char padding[12];
 } ora_triangle;
 
-/* BUILD-DEFINED acceleration structure, consumed as DATA (built by the product's
- * host builder, validated structurally by tests): same byte layout as
- * include/SharedHeader.h:ptb_bvh_node.                                         */
+/* BUILD-DEFINED acceleration structure: same byte layout as include/SharedHeader.h:ptb_bvh_node.
+ * Built by the oracle's own builder (oracle_bvh.c: ora_bvh_build, the specification of the tree);
+ * tests assert that the product's builders produce the same bytes.                              */
 typedef struct ora_bvh_node { /* binary, 64 bytes (include/SharedHeader.h: ptb_bvh_node) */
     float c0[3]; /* child-0 box centre      */
     int32_t child0;
@@ -91,8 +91,17 @@ typedef struct ora_bvh_node4 { /* 4-wide, 128 bytes (ptb_bvh_node4) */
     int32_t pad3;
 } ora_bvh_node4;
 
+/* FLAT form for scenes of <= 32 leaves and <= 64 triangles (include/SharedHeader.h: ptb_bvh_leafbox): the leaves of the
+ * binary tree in leaf order, each with its padded box and the bit mask of its triangles' positions in the ordered array */
+typedef struct ora_bvh_leafbox {
+    float c[3];
+    uint32_t mask_lo; /* triangles first .. first+count-1 of the ordered array, bits 0..31 */
+    float e[3];
+    uint32_t mask_hi; /* bits 32..63 */
+} ora_bvh_leafbox;
+
 typedef struct ora_bvh {
-    const void* nodes; /* ora_bvh_node[n_nodes] when width == 2, ora_bvh_node4[n_nodes] when width == 4 */
+    const void* nodes; /* ora_bvh_node[n_nodes] (width 2), ora_bvh_node4[n_nodes] (width 4), ora_bvh_leafbox[n_nodes] (width 1) */
     int32_t n_nodes;
     const int32_t* tri_order; /* BVH position -> index into the caller's triangle array */
     int32_t n_tris;
@@ -133,6 +142,20 @@ typedef struct ora_counters {
     uint64_t rays_closest, rays_any, nodes, tri_tests, samples;
     uint64_t tri_u, tri_v, tri_t, tri_accept; /* tests that reached the u / v / t stage, accepted */
 } ora_counters;
+
+/* oracle_bvh.c: deterministic binned-SAH build (rules R1-R7 there).  width 2 -> ora_bvh_node[], width 4 -> ora_bvh_node4[]
+ * (<= 2048 triangles), width 1 -> ora_bvh_leafbox[] (<= 32 leaves, <= 64 triangles).  *nodes and *tri_order are malloc'd: release with ora_free.  Returns 0 on success.   */
+typedef struct ora_bvh_params {
+    int32_t max_leaf;    /* 1..8, default 4 */
+    float pad_rel;       /* boxes grow by pad_rel * scene diagonal, default 1e-4 */
+    int32_t n_bins;      /* default 16 */
+    int32_t smem_nodes;  /* breadth-first prefix, default 1024 */
+    float traverse_cost; /* SAH cost of a node visit relative to a triangle test, default 1.2 */
+} ora_bvh_params;
+void ora_bvh_params_default(ora_bvh_params* p);
+int ora_bvh_build(const ora_triangle* tris, int n_tris, const ora_bvh_params* params, int width, void** nodes,
+                  int* n_nodes, int32_t** tri_order, int* depth, int* bfs_nodes);
+void ora_free(void* p);
 
 /* RaytraceTest.cpp:87-198 */
 int ora_load_model(const char* path, ora_triangle* tris, int tri_cap, ora_material* mats, int mat_cap,

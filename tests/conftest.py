@@ -45,11 +45,36 @@ def cornell(ob):
 
 
 @pytest.fixture(scope="session")
-def cornell_bvh(pt, ob, cornell):
+def cornell_bvh(ob, cornell):
+    """The ORACLE's own tree for the Cornell box (oracle/oracle_bvh.c) in the form the product picks for that scene
+    (FLAT: 18 leaf boxes).  Product trees are compared with it byte for byte (tests/test_host.py)."""
     tris, _ = cornell
-    b = pt.build_bvh_host(tris)
+    b = ob.build_bvh(tris)
     bvh, keep = ob.make_bvh(b["nodes"], b["tri_order"])
     return b, bvh, keep
+
+
+def oracle_tree_for_mode(ob, tris, mode, cache={}):
+    """The oracle's own tree in the form the product walks for `mode` on a default-built scene: FLAT scenes keep their
+    4-wide tree too and use it for DIRECT (coherent rays); see ptb_scene_mode_width."""
+    auto = ob.build_bvh(tris)
+    width = 4 if (auto["width"] == 1 and mode == 2) else auto["width"]
+    b = auto if width == auto["width"] else ob.build_bvh(tris, width=width)
+    bvh, keep = ob.make_bvh(b["nodes"], b["tri_order"])
+    return bvh, keep, b
+
+
+def oracle_tree(ob, tris, width=None, **params):
+    """(ora_bvh, keepalive, dict) built by the oracle's own builder; params = ora_bvh_params fields."""
+    b = ob.build_bvh(tris, ob.bvh_params(**params) if params else None, width=width)
+    bvh, keep = ob.make_bvh(b["nodes"], b["tri_order"])
+    return bvh, keep, b
+
+
+def assert_same_tree(nodes, order, b):
+    """the product's tree (nodes, tri_order) equals the oracle's, byte for byte"""
+    assert np.ascontiguousarray(nodes).view(np.uint8).tobytes() == b["nodes"].view(np.uint8).tobytes()
+    assert np.array_equal(np.asarray(order), b["tri_order"])
 
 
 @pytest.fixture(scope="session")

@@ -80,20 +80,24 @@ def scene_facts():
 
 def oracle_small():
     from oracle import binding as ob
-    import oclpathtracer_b200 as pt
 
     tris, mats = ob.load_model(os.path.join(ROOT, "data", "cornellbox.bin"))
-    b = pt.build_bvh_host(tris)
-    bvh, _keep = ob.make_bvh(b["nodes"], b["tri_order"])
     p1, ea, eb = ob.light_from_quad(tris, 5)
-    out = {"bvh_nodes": b["nodes"].view(np.uint8).reshape(-1, b["nodes"].dtype.itemsize), "bvh_order": b["tri_order"]}
-    for name, mode in (("primary", 0), ("ao", 1), ("direct", 2), ("path", 3)):
-        prm = ob.default_params(32, 32, n_frames=3, mode=mode, accum=ob.ACCUM_LINEAR, use_bvh=1, max_depth=8,
-                                light_p1=p1, light_ea=ea, light_eb=eb)
-        fb, st, ctr = ob.render(prm, tris, mats, bvh=bvh, want_stats=True)
-        out[f"{name}_fb"] = fb
-        out[f"{name}_stats"] = st.view(np.uint32).reshape(-1, 8)
-        out[f"{name}_ctr"] = np.array([ctr[k] for k in ("rays_closest", "rays_any", "nodes", "tri_tests")], np.uint64)
+    out = {}
+    # the oracle's OWN trees (oracle_bvh.c) in the three forms: FLAT (what the product picks for the Cornell box; the
+    # un-suffixed keys), 4-wide and binary (force_width = 4 | 2)
+    for width, sfx in ((1, ""), (4, "_w4"), (2, "_w2")):
+        b = ob.build_bvh(tris, width=width)
+        bvh, _keep = ob.make_bvh(b["nodes"], b["tri_order"])
+        out["bvh_nodes" + sfx] = b["nodes"].view(np.uint8).reshape(-1, b["nodes"].dtype.itemsize)
+        out["bvh_order" + sfx] = b["tri_order"]
+        for name, mode in (("primary", 0), ("ao", 1), ("direct", 2), ("path", 3)):
+            prm = ob.default_params(32, 32, n_frames=3, mode=mode, accum=ob.ACCUM_LINEAR, use_bvh=1, max_depth=8,
+                                    light_p1=p1, light_ea=ea, light_eb=eb)
+            fb, st, ctr = ob.render(prm, tris, mats, bvh=bvh, want_stats=True)
+            out[f"{name}_fb{sfx}"] = fb
+            out[f"{name}_stats{sfx}"] = st.view(np.uint32).reshape(-1, 8)
+            out[f"{name}_ctr{sfx}"] = np.array([ctr[k] for k in ("rays_closest", "rays_any", "nodes", "tri_tests")], np.uint64)
     prm = ob.default_params(32, 32, first_frame=0, n_frames=5, mode=3, accum=ob.ACCUM_REFERENCE, use_bvh=0)
     fb, _, _ = ob.render(prm, tris, mats)
     out["path_reference_accum_fb"] = fb

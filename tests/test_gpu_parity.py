@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, SCENE, bits, oracle_params
+from conftest import GOLDEN, SCENE, assert_same_tree, bits, oracle_params, oracle_tree, oracle_tree_for_mode
 
 pytestmark = pytest.mark.gpu
 
@@ -106,7 +106,7 @@ def test_trace_hit_ids_and_visit_counts(dev, pt, ob, cornell, cornell_bvh, scene
             np.testing.assert_array_equal(bits(g_bvh[f]), bits(o_bru[f]))
     else:
         np.testing.assert_array_equal(g_bvh["tri"] >= 0, o_bru["tri"] >= 0)
-    assert (g_bvh["tests"] <= 36).all() and g_bvh["visits"].max() <= 9
+    assert (g_bvh["tests"] <= 36).all() and g_bvh["visits"].max() <= 18  # FLAT form: visits = leaf boxes passed
 
 
 # ---- the hot path: every mode x integrator x accel ----------------------------------------------------
@@ -117,9 +117,10 @@ MODES = {"primary": 0, "ao": 1, "direct": 2, "path": 3}
 @pytest.mark.parametrize("integrator", ["mega", "wavefront"])
 @pytest.mark.parametrize("accel", ["bvh", "brute"])
 @pytest.mark.parametrize("mode", list(MODES))
-def test_render_bit_exact(dev, pt, ob, cornell, cornell_bvh, scene, mode, accel, integrator):
+def test_render_bit_exact(dev, pt, ob, cornell, scene, mode, accel, integrator):
     tris, mats = cornell
-    _, bvh, _ = cornell_bvh
+    bvh, _keep, ot = oracle_tree_for_mode(ob, tris, MODES[mode])
+    assert scene.mode_width(MODES[mode]) == ot["width"] == (4 if mode == "direct" else 1)
     w, h, nf = 96, 80, 3
     use_bvh = accel == "bvh"
     prm = pt.default_params(width=w, height=h, n_frames=nf, mode=MODES[mode], accum=pt.ACCUM_LINEAR, max_depth=8,
@@ -142,17 +143,47 @@ def test_render_bit_exact(dev, pt, ob, cornell, cornell_bvh, scene, mode, accel,
         assert ctr[k] == octr[k], k
 
 
-def test_golden_vectors_on_device(dev, pt, cornell, scene):
+@pytest.mark.parametrize("width", [1, 4, 2])
+def test_golden_vectors_on_device(dev, pt, cornell, width):
+    """tests/golden/oracle_small.npz: the oracle's own trees and 32x32 renders in the three scene forms
+    (FLAT = what ptb_scene_create picks for the Cornell box, 4-wide and binary forced)."""
     g = np.load(os.path.join(GOLDEN, "oracle_small.npz"))
-    nodes, order = scene.bvh()
-    assert nodes.view(np.uint8).tobytes() == g["bvh_nodes"].tobytes() and order.tolist() == g["bvh_order"].tolist()
     tris, mats = cornell
+    sc = dev.scene(tris, mats, pt.bvh_params(force_width=0 if width == 1 else width))
+    sfx = {1: "", 4: "_w4", 2: "_w2"}[width]
+    assert sc.info()["width"] == width
+    nodes, order = sc.bvh()
+    assert nodes.view(np.uint8).tobytes() == g["bvh_nodes" + sfx].tobytes() and order.tolist() == g["bvh_order" + sfx].tolist()
     for name, mode in MODES.items():
-        prm = pt.default_params(width=32, height=32, n_frames=3, mode=mode, accum=pt.ACCUM_LINEAR, max_depth=8, collect_stats=1)
-        fb, st, ctr = dev.render_host(tris, mats, prm, want_stats=True)
-        assert fb.tobytes() == g[f"{name}_fb"].tobytes(), name
-        assert st.tobytes() == g[f"{name}_stats"].tobytes(), name
-        assert [ctr[k] for k in ("rays_closest", "rays_any", "nodes", "tri_tests")] == g[f"{name}_ctr"].tolist()
+        sfx = {1: "", 4: "_w4", 2: "_w2"}[sc.mode_width(mode)]  # a FLAT scene walks its 4-wide tree for DIRECT
+        for integ in (pt.INTEGRATOR_MEGAKERNEL, pt.INTEGRATOR_WAVEFRONT):
+            prm = pt.default_params(width=32, height=32, n_frames=3, mode=mode, accum=pt.ACCUM_LINEAR, max_depth=8, collect_stats=1,
+                                    integrator=integ)
+            frame, stats = dev.buffer(32 * 32 * 16), dev.buffer(32 * 32 * 32)
+            ctr = dev.render(sc, prm, frame, stats, want_counters=True)
+            fb, st = frame.read(np.float32), stats.read(pt.STATS_DTYPE)
+            frame.close(); stats.close()
+            assert fb.tobytes() == g[f"{name}_fb{sfx}"].tobytes(), (name, integ)
+            assert st.tobytes() == g[f"{name}_stats{sfx}"].tobytes(), (name, integ)
+            assert [ctr[k] for k in ("rays_closest", "rays_any", "nodes", "tri_tests")] == g[f"{name}_ctr{sfx}"].tolist()
+    sc.close()
+
+
+@pytest.mark.parametrize("width", [4, 2])
+@pytest.mark.parametrize("any_hit", [False, True])
+def test_trace_forced_tree_forms(dev, pt, ob, cornell, width, any_hit):
+    """the 4-wide and binary while-while traversals on the Cornell box (force_width), against the oracle walking its own tree"""
+    tris, mats = cornell
+    sc = dev.scene(tris, mats, pt.bvh_params(force_width=width))
+    bvh, _keep, ot = oracle_tree(ob, tris, width=width)
+    assert_same_tree(*sc.bvh(), ot)
+    o, d = _rays(100_000, 12)
+    tmax = np.float32(2.5) if any_hit else np.float32(1e20)
+    g = dev.trace(sc, o, d, tmax, accel=pt.ACCEL_BVH, any_hit=any_hit)
+    r = ob.trace(tris, o, d, tmax, bvh=bvh, any_hit=any_hit)
+    for f in ("tri", "t", "u", "v", "visits", "tests"):
+        np.testing.assert_array_equal(bits(g[f]), bits(r[f]), err_msg=f)
+    sc.close()
 
 
 # ---- the reference's own flow: GenerateColors launched frame by frame ---------------------------------
@@ -240,8 +271,7 @@ def test_single_triangle_and_miss_paths(dev, pt, ob, cornell):
         for integ in (pt.INTEGRATOR_MEGAKERNEL, pt.INTEGRATOR_WAVEFRONT):
             prm.integrator = integ
             fb, st, ctr = dev.render_host(one, mats, prm, want_stats=True)
-            b = pt.build_bvh_host(one)
-            bvh, _keep = ob.make_bvh(b["nodes"], b["tri_order"])
+            bvh, _keep, _ = oracle_tree_for_mode(ob, one, mode)
             oprm = oracle_params(ob, tris, 64, 64, n_frames=2, mode=mode, accum=1, max_depth=4, use_bvh=1)
             ofb, ost, octr = ob.render(oprm, one, mats, bvh=bvh, want_stats=True)
             np.testing.assert_array_equal(bits(fb), bits(ofb))
@@ -270,7 +300,8 @@ def _tessellated_body(dev, pt, ob, cornell):
     assert info["n_nodes"] > info["smem_nodes"] == 128 and info["width"] == 2
     dev.set_tuning(4, 128)  # stage the whole 128-node prefix (default cap is 64)
     nodes, order = sc.bvh()
-    bvh, _keep = ob.make_bvh(nodes, order)
+    bvh, _keep, ot = oracle_tree(ob, big, width=2, smem_nodes=128)  # the oracle's own tree; the product's must be the same
+    assert_same_tree(nodes, order, ot)
     w, h = 64, 64
     for mode in (0, 1, 2, 3):
         for integ in (pt.INTEGRATOR_MEGAKERNEL, pt.INTEGRATOR_WAVEFRONT):
@@ -321,10 +352,38 @@ def test_c1_primary_512_full_size_vs_oracle(dev, pt, ob, cornell, cornell_bvh, s
     assert ctr["rays_closest"] == 512 * 512
 
 
-def test_c2_ao_1024_full_size_properties(dev, pt, scene):
-    """configs[1]: AO 1024x1024, 16 rays/pixel.  BVH == brute force == wavefront, bit for bit; values are k/16."""
+def _full_size_vs_oracle(dev, pt, ob, cornell, scene, w, h, mode, frames, shard=None, **kw):
+    """One full-size frame range of a BASELINE configuration, rendered through the C-ABI, against the ORACLE walking its own
+    tree: radiance bits, per-pixel hit ids / t bits / node-visit counts / id hashes, and the ray / node / test counters."""
+    tris, mats = cornell
+    bvh, _keep, ot = oracle_tree_for_mode(ob, tris, mode)
+    assert scene.mode_width(mode) == ot["width"]
+    p1, ea, eb = pt.light_from_quad(tris, 5)
+    skw = dict(shard_index=shard[0], shard_count=shard[1], shard_block=shard[2]) if shard else {}
+    for first, n in frames:
+        prm = pt.default_params(width=w, height=h, first_frame=first, n_frames=n, mode=mode, accum=pt.ACCUM_LINEAR, collect_stats=1,
+                                light_p1=p1, light_ea=ea, light_eb=eb, **skw, **kw)
+        nl = pt.local_pixels(prm)
+        frame, stats = dev.buffer(nl * 16), dev.buffer(nl * 32)
+        ctr = dev.render(scene, prm, frame, stats, want_counters=True)
+        fb, st = frame.read(np.float32).reshape(-1, 4), stats.read(pt.STATS_DTYPE)
+        frame.close(); stats.close()
+        oprm = ob.default_params(w, h, first_frame=first, n_frames=n, mode=mode, accum=ob.ACCUM_LINEAR, use_bvh=1,
+                                 light_p1=p1, light_ea=ea, light_eb=eb, **skw, **kw)
+        ofb, ost, octr = ob.render(oprm, tris, mats, bvh=bvh, want_stats=True)
+        np.testing.assert_array_equal(bits(fb), bits(ofb), err_msg=f"radiance, frames {first}+{n}")
+        for f in ost.dtype.names:
+            np.testing.assert_array_equal(st[f], ost[f], err_msg=f"{f}, frames {first}+{n}")
+        for k in ("rays_closest", "rays_any", "nodes", "tri_tests", "samples"):
+            assert ctr[k] == octr[k], (k, first, n)
+    return fb, ctr
+
+
+def test_c2_ao_1024_full_size_vs_oracle(dev, pt, ob, cornell, scene):
+    """configs[1] at FULL size: AO 1024x1024, 16 rays/pixel -- the whole frame against the oracle (17.8 Mrays), then the
+    size-independent properties: BVH == brute force == wavefront bit for bit, values are k/16."""
+    a, ca = _full_size_vs_oracle(dev, pt, ob, cornell, scene, 1024, 1024, pt.MODE_AO, [(0, 1)], ao_samples=16)
     kw = dict(width=1024, height=1024, n_frames=1, mode=pt.MODE_AO, accum=pt.ACCUM_LINEAR, ao_samples=16)
-    a, ca = _render(dev, pt, scene, accel=pt.ACCEL_BVH, integrator=pt.INTEGRATOR_MEGAKERNEL, **kw)
     b, cb = _render(dev, pt, scene, accel=pt.ACCEL_BRUTE, integrator=pt.INTEGRATOR_MEGAKERNEL, **kw)
     c, cc = _render(dev, pt, scene, accel=pt.ACCEL_BVH, integrator=pt.INTEGRATOR_WAVEFRONT, **kw)
     assert a.tobytes() == b.tobytes() == c.tobytes()
@@ -334,8 +393,10 @@ def test_c2_ao_1024_full_size_properties(dev, pt, scene):
     assert np.array_equal(a[:, 0], a[:, 1]) and np.array_equal(a[:, 3], np.ones(len(a), np.float32))
 
 
-def test_c3_direct_1080p_properties(dev, pt, scene):
-    """configs[2] geometry at 4 of its 64 spp: integrators and accelerators agree bit for bit."""
+def test_c3_direct_1080p_full_size_vs_oracle(dev, pt, ob, cornell, scene):
+    """configs[2] at FULL size: direct lighting 1920x1080 -- frames 0-1 and the LAST frame of the 64-spp range (63) against
+    the oracle, every pixel; then integrators and accelerators agree bit for bit on 4 frames."""
+    _full_size_vs_oracle(dev, pt, ob, cornell, scene, 1920, 1080, pt.MODE_DIRECT, [(0, 2), (63, 1)])
     kw = dict(width=1920, height=1080, n_frames=4, mode=pt.MODE_DIRECT, accum=pt.ACCUM_LINEAR)
     a, ca = _render(dev, pt, scene, accel=pt.ACCEL_BVH, integrator=pt.INTEGRATOR_MEGAKERNEL, **kw)
     b, cb = _render(dev, pt, scene, accel=pt.ACCEL_BRUTE, integrator=pt.INTEGRATOR_WAVEFRONT, **kw)
@@ -343,9 +404,12 @@ def test_c3_direct_1080p_properties(dev, pt, scene):
     assert np.isfinite(a).all() and a[:, :3].min() >= 0
 
 
-def test_c4_path_4k_properties(dev, pt, scene):
-    """configs[3] geometry (4K, max depth 8) at 2 of its 256 spp: megakernel == wavefront; linearity of the
-    frame mean: mean(f0,f1) == (mean(f0) + mean(f1)) / 2 computed from single-frame renders."""
+def test_c4_path_4k_full_size_vs_oracle(dev, pt, ob, cornell, scene):
+    """configs[3] at FULL size: 3840x2160, max depth 8 -- one whole 4K frame (frame 0: 8.3 M paths, ~30 M rays) and the LAST
+    frame of the 256-spp range (255, a 1/4 tile shard) against the oracle; then megakernel == wavefront and linearity of
+    the frame mean: mean(f0,f1) == (f0 + f1) / 2 from single-frame renders."""
+    _full_size_vs_oracle(dev, pt, ob, cornell, scene, 3840, 2160, pt.MODE_PATH, [(0, 1)], max_depth=8)
+    _full_size_vs_oracle(dev, pt, ob, cornell, scene, 3840, 2160, pt.MODE_PATH, [(255, 1)], shard=(1, 4, 64), max_depth=8)
     kw = dict(width=3840, height=2160, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR, max_depth=8)
     a, ca = _render(dev, pt, scene, n_frames=2, integrator=pt.INTEGRATOR_MEGAKERNEL, **kw)
     b, cb = _render(dev, pt, scene, n_frames=2, integrator=pt.INTEGRATOR_WAVEFRONT, **kw)
@@ -608,15 +672,16 @@ def test_reference_device_tests_over_shim():
 
 
 def test_c5_two_million_triangles_properties(dev, pt, ob, cornell):
-    """configs[4] scene at full size (18 quads x 236^2 x 2 = 2,005,056 triangles), reduced image.
-    Size-independent properties: radiance does not depend on the acceleration structure (host SAH tree ==
-    device LBVH tree == megakernel == wavefront, bit for bit), sampled hit ids equal the reference's
-    brute-force loop over all 2M triangles, and a sampled set of pixels equals the CPU oracle on the SAH tree."""
+    """configs[4] at FULL size: the 2,005,056-triangle scene (18 quads x 236^2 x 2) at 3840x2160, max depth 8.
+    A 1/16 tile shard of frame 0 and a 1/64 shard of the LAST frame of the 64-spp range (63) equal the CPU oracle walking
+    its own tree (which the product's tree must equal byte for byte): radiance bits, hit ids, node-visit counts, counters.
+    Size-independent properties: radiance does not depend on the acceleration structure (host SAH tree == device LBVH
+    tree == megakernel == wavefront, bit for bit); sampled hit ids equal the reference's brute-force loop over all 2M triangles."""
     tris, mats = cornell
     big = pt.tessellate(tris, 236)
     assert len(big) == 2_005_056
     p1, ea, eb = pt.light_from_quad(tris, 5)
-    w, h = 640, 360
+    w, h = 3840, 2160
     kw = dict(width=w, height=h, n_frames=1, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR, max_depth=8,
               light_p1=p1, light_ea=ea, light_eb=eb)
     frames = {}
@@ -634,17 +699,23 @@ def test_c5_two_million_triangles_properties(dev, pt, ob, cornell):
     for f in ("tri", "t", "u", "v"):
         np.testing.assert_array_equal(bits(g[f]), bits(r[f]))
     assert (r["tests"] == len(big)).all() and g["tests"].max() < 200
-    # a shard of the image against the CPU oracle walking the same tree
+    # a shard of the image against the CPU oracle walking its own tree (which the product's must equal)
     nodes, order = sah.bvh()
-    bvh, _keep = ob.make_bvh(nodes, order)
-    shard = dict(shard_index=3, shard_count=60, shard_block=64)
-    fbuf = dev.buffer(pt.local_pixels(pt.default_params(**kw, **shard)) * 16)
-    dev.render(sah, pt.default_params(**kw, **shard), fbuf)
-    got = fbuf.read(np.float32).reshape(-1, 4)
-    fbuf.close()
-    okw = dict(n_frames=1, mode=3, accum=1, max_depth=8, use_bvh=1, light_p1=p1, light_ea=ea, light_eb=eb, **shard)
-    want, _, _ = ob.render(ob.default_params(w, h, **okw), big, mats, bvh=bvh)
-    np.testing.assert_array_equal(bits(got), bits(want))
+    bvh, _keep, ot = oracle_tree(ob, big)
+    assert_same_tree(nodes, order, ot)
+    for first, shard in ((0, dict(shard_index=5, shard_count=16, shard_block=64)), (63, dict(shard_index=40, shard_count=64, shard_block=64))):
+        prm = pt.default_params(**{**kw, "first_frame": first}, collect_stats=1, **shard)
+        nl = pt.local_pixels(prm)
+        fbuf, sbuf = dev.buffer(nl * 16), dev.buffer(nl * 32)
+        ctr = dev.render(sah, prm, fbuf, sbuf, want_counters=True)
+        got, gst = fbuf.read(np.float32).reshape(-1, 4), sbuf.read(pt.STATS_DTYPE)
+        fbuf.close(); sbuf.close()
+        okw = dict(first_frame=first, n_frames=1, mode=3, accum=1, max_depth=8, use_bvh=1, light_p1=p1, light_ea=ea, light_eb=eb, **shard)
+        want, wst, octr = ob.render(ob.default_params(w, h, **okw), big, mats, bvh=bvh, want_stats=True)
+        np.testing.assert_array_equal(bits(got), bits(want))
+        assert gst.tobytes() == wst.tobytes()
+        for k in ("rays_closest", "nodes", "tri_tests", "samples"):
+            assert ctr[k] == octr[k], (k, first)
     sah.close()
     lb = dev.scene(big, mats, gpu_build=True)
     frame = dev.buffer(w * h * 16)
@@ -756,12 +827,11 @@ def test_launch1d_frame_ahead_batching(dev, pt, ob, cornell):
 
 
 @pytest.mark.parametrize("integrator", ["mega", "wavefront"])
-def test_ragged_and_degenerate_shapes(dev, pt, ob, cornell, cornell_bvh, scene, integrator):
+def test_ragged_and_degenerate_shapes(dev, pt, ob, cornell, scene, integrator):
     """Edge shapes: a single pixel, sizes below one warp / not a multiple of the CTA, a shard that owns a ragged tail,
     one AO ray, depth 1, a batch size that does not divide the frame count, frame indices near INT_MAX (the seed is
     gid + 1103515245*frame + 12345 in uint32 arithmetic, GenerateColors.cl:305-308).  All bit-exact vs the oracle."""
     tris, mats = cornell
-    _, bvh, _ = cornell_bvh
     integ = pt.INTEGRATOR_MEGAKERNEL if integrator == "mega" else pt.INTEGRATOR_WAVEFRONT
     cases = [
         dict(w=1, h=1, mode=3, n_frames=5, fpb=2, first=0, max_depth=16),
@@ -772,6 +842,7 @@ def test_ragged_and_degenerate_shapes(dev, pt, ob, cornell, cornell_bvh, scene, 
         dict(w=40, h=40, mode=0, n_frames=1, fpb=1, first=0, shard=(6, 7, 64)),
     ]
     for cs in cases:
+        bvh, _keep, _ = oracle_tree_for_mode(ob, tris, cs["mode"])
         kw = dict(n_frames=cs["n_frames"], first_frame=cs["first"], mode=cs["mode"], max_depth=cs.get("max_depth", 8),
                   ao_samples=cs.get("ao_samples", 16))
         if "shard" in cs:

@@ -96,9 +96,44 @@ def _validate_bvh(pt, tris, b, pad_min=0.0):
     assert covered.all() and seen_nodes.all()
 
 
-def test_bvh_structure_cornell(pt, cornell):
+@pytest.mark.parametrize("k,kw", [(1, {}), (4, {}), (4, {"max_leaf": 2, "smem_nodes": 64}), (12, {}), (12, {"traverse_cost": 2.5, "n_bins": 8}), (236, {})])
+def test_product_tree_equals_oracle_tree(pt, ob, cornell, k, kw):
+    """The oracle has its own deterministic builder (oracle/oracle_bvh.c, rules R1-R7); the product's host builder
+    (csrc/bvh_build.cpp) must produce the same bytes in every form the scene qualifies for -- node-visit parity then does
+    not lean on the product's own tree.  k = 236 is the 2,005,056-triangle scene of configs[4]."""
+    tris, _ = cornell
+    scene = tris if k == 1 else pt.tessellate(tris, k)
+    widths = [2] + ([4] if len(scene) <= 2048 else []) + ([1] if len(scene) <= 64 else [])
+    for width in widths:
+        o = ob.build_bvh(scene, ob.bvh_params(**kw) if kw else None, width=width)
+        p = pt.build_bvh_host(scene, pt.bvh_params(**kw) if kw else None, width=width)
+        assert p["nodes"].view(np.uint8).tobytes() == o["nodes"].view(np.uint8).tobytes(), (k, width)
+        assert np.array_equal(p["tri_order"], o["tri_order"]) and p["depth"] == o["depth"] and p["smem_nodes"] == o["bfs_nodes"]
+
+
+def test_flat_form_of_tiny_scenes(pt, ob, cornell):
+    """FLAT form (<= 32 leaves, <= 64 triangles): one record per leaf in leaf order, masks partition the triangle positions."""
     tris, _ = cornell
     b = pt.build_bvh_host(tris)
+    assert b["width"] == 1 and len(b["nodes"]) == 18 and b["depth"] == 1
+    m = b["nodes"]["mask_lo"].astype(np.uint64) | (b["nodes"]["mask_hi"].astype(np.uint64) << np.uint64(32))
+    assert int(np.bitwise_or.reduce(m)) == (1 << 36) - 1 and sum(bin(int(x)).count("1") for x in m) == 36
+    assert all(int(m[i]) < int(m[i + 1]) for i in range(len(m) - 1))  # leaf order == triangle order
+    b2 = pt.build_bvh_host(tris, width=2)
+    for i, rec in enumerate(b["nodes"]):  # every leaf box contains its triangles (padded)
+        pos = [k for k in range(36) if (int(m[i]) >> k) & 1]
+        v = np.concatenate([np.stack([tris[n][b["tri_order"][pos]][:, :3] for n in ("p1", "p2", "p3")])])
+        assert (v.reshape(-1, 3) >= rec["c"] - rec["e"]).all() and (v.reshape(-1, 3) <= rec["c"] + rec["e"]).all()
+    np.testing.assert_array_equal(b2["tri_order"], b["tri_order"])
+    with pytest.raises(pt.PtbError, match="FLAT"):
+        pt.build_bvh_host(pt.tessellate(tris, 2), width=1)
+    one = pt.build_bvh_host(tris[:1], width=1)
+    assert len(one["nodes"]) == 1 and one["nodes"]["mask_lo"][0] == 1
+
+
+def test_bvh_structure_cornell(pt, cornell):
+    tris, _ = cornell
+    b = pt.build_bvh_host(tris, width=4)
     assert b["width"] == 4 and b["smem_nodes"] == len(b["nodes"]) <= 17 and 1 <= b["depth"] <= 8
     _validate_bvh(pt, tris, b, pad_min=5e-4)  # default pad = 1e-4 * diagonal(9.6) ~ 9.6e-4
     b2 = pt.build_bvh_host(tris, width=2)

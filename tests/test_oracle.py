@@ -121,10 +121,10 @@ def test_bvh_equals_brute_force(ob, cornell, cornell_bvh, mode):
     assert cb["nodes"] > 0 and cb["tri_tests"] < ca["tri_tests"]
 
 
-@pytest.mark.parametrize("width", [4, 2])
-def test_trace_random_rays_brute_vs_bvh(pt, ob, cornell, width):
+@pytest.mark.parametrize("width", [1, 4, 2])
+def test_trace_random_rays_brute_vs_bvh(ob, cornell, width):
     tris, _ = cornell
-    b = pt.build_bvh_host(tris, width=width)
+    b = ob.build_bvh(tris, width=width)
     bvh, _keep = ob.make_bvh(b["nodes"], b["tri_order"])
     rng = np.random.default_rng(3)
     n = 200_000
@@ -202,20 +202,27 @@ def test_tessellation_matches_product_and_preserves_hits(pt, ob, cornell):
     assert (s0["quad"] == s1["quad"]).mean() > 0.995
 
 
-def test_golden_small_renders(pt, ob, cornell):
-    """The committed oracle vectors still reproduce (pins the oracle against drift)."""
+@pytest.mark.parametrize("width", [1, 4, 2])
+def test_golden_small_renders(pt, ob, cornell, width):
+    """The committed oracle vectors still reproduce (pins the oracle -- builder and traversal -- against drift), and the
+    product's host builder produces the same tree bytes as the oracle's own."""
     tris, mats = cornell
     g = np.load(os.path.join(GOLDEN, "oracle_small.npz"))
-    b = pt.build_bvh_host(tris)
-    assert b["nodes"].view(np.uint8).tobytes() == g["bvh_nodes"].tobytes()
-    np.testing.assert_array_equal(b["tri_order"], g["bvh_order"])
+    sfx = {1: "", 4: "_w4", 2: "_w2"}[width]
+    b = ob.build_bvh(tris, width=width)
+    assert b["nodes"].view(np.uint8).tobytes() == g["bvh_nodes" + sfx].tobytes()
+    np.testing.assert_array_equal(b["tri_order"], g["bvh_order" + sfx])
+    pb = pt.build_bvh_host(tris, width=width)
+    assert pb["nodes"].view(np.uint8).tobytes() == b["nodes"].view(np.uint8).tobytes() and np.array_equal(pb["tri_order"], b["tri_order"])
     bvh, _keep = ob.make_bvh(b["nodes"], b["tri_order"])
     for name, mode in (("primary", 0), ("ao", 1), ("direct", 2), ("path", 3)):
         prm = oracle_params(ob, tris, 32, 32, n_frames=3, mode=mode, accum=ob.ACCUM_LINEAR, use_bvh=1, max_depth=8)
         fb, st, ctr = ob.render(prm, tris, mats, bvh=bvh, want_stats=True)
-        assert fb.tobytes() == g[f"{name}_fb"].tobytes(), name
-        assert st.tobytes() == g[f"{name}_stats"].tobytes(), name
-        assert [ctr[k] for k in ("rays_closest", "rays_any", "nodes", "tri_tests")] == g[f"{name}_ctr"].tolist()
+        assert fb.tobytes() == g[f"{name}_fb{sfx}"].tobytes(), name
+        assert st.tobytes() == g[f"{name}_stats{sfx}"].tobytes(), name
+        assert [ctr[k] for k in ("rays_closest", "rays_any", "nodes", "tri_tests")] == g[f"{name}_ctr{sfx}"].tolist()
+    if width != 1:
+        return
     fb, _, _ = ob.render(ob.default_params(32, 32, first_frame=0, n_frames=5, mode=3, accum=0, use_bvh=0), tris, mats)
     assert fb.tobytes() == g["path_reference_accum_fb"].tobytes()
 
