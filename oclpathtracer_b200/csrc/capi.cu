@@ -520,11 +520,6 @@ extern "C" int ptb_scene_info(ptb_scene* s, int* n_nodes, int* n_tris, int* dept
 }
 
 extern "C" int ptb_scene_bvh_width(ptb_scene* s) { return s ? s->width : 0; }
-extern "C" int ptb_scene_mode_width(ptb_scene* s, int mode) {
-    if (!s) return 0;
-    const int c = mode_class(s, mode);
-    return c == ptd::PTD_FLAT ? 1 : c == ptd::PTD_SMALL4 ? 4 : 2;
-}
 
 extern "C" int ptb_scene_copy_bvh(ptb_scene* s, void* nodes, int32_t* tri_order) {
     if (!s) return fail(PTB_E_INVALID, "ptb_scene_copy_bvh: null scene");
@@ -553,6 +548,12 @@ extern "C" int ptb_scene_copy_bvh(ptb_scene* s, void* nodes, int32_t* tri_order)
 static int mode_class(const ptb_scene* s, int mode) {
     if (s->cls == ptd::PTD_FLAT && s->d_nodes4 && mode == PTB_MODE_DIRECT) return ptd::PTD_SMALL4;
     return s->cls;
+}
+
+extern "C" int ptb_scene_mode_width(ptb_scene* s, int mode) {
+    if (!s) return 0;
+    const int c = mode_class(s, mode);
+    return c == ptd::PTD_FLAT ? 1 : c == ptd::PTD_SMALL4 ? 4 : 2;
 }
 
 static ptd::SceneDev scene_dev(const ptb_scene* s, int cls) {
