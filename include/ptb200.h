@@ -120,6 +120,9 @@ int ptb_light_from_quad(const ptb_triangle* tris, int n_tris, int quad, float p1
 void ptb_free(void* p);
 /* RaytraceTest.cpp:78-83,:277-287: sqrt, x255, truncate, clamp -> ASCII "P3" */
 int ptb_to_rgb8(const float* rgba, int n_pixels, uint8_t* rgb);
+/* the same transform on the device (identical bytes): float4 frame buffer -> 3 bytes per pixel in rgb (>= 3 * n_pixels
+ * bytes, 16-byte aligned), asynchronous on the frame buffer's device stream */
+int ptb_buffer_to_rgb8(ptb_buffer* frame, int n_pixels, ptb_buffer* rgb);
 int ptb_write_ppm(const char* path, const float* rgba, int width, int height);
 
 /* ---- resident scene: triangles re-laid out + BVH (BUILD-DEFINED) --------------------- */
@@ -223,6 +226,11 @@ int ptb_host_free(void* p);
  * and returns the totals since the previous read.  kernel_launches counts this
  * library's own kernel launches (always on).                                      */
 int ptb_device_profile(ptb_device* dev, int enable);
+/* Ray / node / test counters of the device.  By default every render call starts them at zero (and returns them when
+ * asked).  cumulative = 1: the counters keep adding up over render calls until this function reads them (out != NULL:
+ * synchronises, returns the totals since the previous read and clears them) -- exact ray counts over a whole timed
+ * region without a synchronisation inside it.  cumulative = 0 restores the default; -1 leaves the mode as it is.      */
+int ptb_device_counters(ptb_device* dev, int cumulative, ptb_counters* out);
 /* experiment knobs for A/B measurements (results never change).  index: 1 = log2 multiplier of
  * the frame-ahead batch of ptb_launch1d; 2 = 2: keep the traversal stack of large scenes in shared memory; 3 = CTA
  * size 64 | 32 (default 128); 4 = BVH nodes staged per CTA for large scenes (default 64); 5 = 1: one sample per

@@ -100,7 +100,7 @@ EXPORTS = [
     "ptb_render_params_default", "ptb_render_local_pixels", "ptb_render", "ptb_render_host",
     "ptb_buffer_ipc_export", "ptb_buffer_ipc_import", "ptb_render_gather",
     "ptb_render_host_async", "ptb_job_wait", "ptb_host_alloc", "ptb_host_free", "ptb_trace",
-    "ptb_device_profile", "ptb_device_profile_read", "ptb_device_set_tuning", "ptb_test_sincos", "ptb_test_pow", "ptb_test_ieee", "ptb_test_rng", "ptb_test_camera",
+    "ptb_device_profile", "ptb_device_counters", "ptb_buffer_to_rgb8", "ptb_device_profile_read", "ptb_device_set_tuning", "ptb_test_sincos", "ptb_test_pow", "ptb_test_ieee", "ptb_test_rng", "ptb_test_camera",
 ]
 
 
@@ -140,6 +140,8 @@ def lib():
         L.ptb_bvh_build_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6
         L.ptb_scene_bvh_width.argtypes = [C.c_void_p]
         L.ptb_scene_mode_width.argtypes = [C.c_void_p, C.c_int]
+        L.ptb_device_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ptb_buffer_to_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ptb_scene_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptb_scene_create_gpu.argtypes = L.ptb_scene_create.argtypes
         L.ptb_scene_info.argtypes = [C.c_void_p] + [C.c_void_p] * 4
@@ -338,6 +340,12 @@ class Device:
         _check(lib().ptb_device_profile_read(self._h, C.byref(ti), C.byref(tr), C.byref(nb), C.byref(nk)))
         return {"integrator_ms": ti.value, "resolve_ms": tr.value, "batches": nb.value, "kernel_launches": nk.value}
 
+    def counters(self, cumulative=-1, read=True):
+        """ptb_device_counters: switch the cumulative mode (1 | 0 | -1 = leave) and/or read + clear the totals."""
+        ctr = Counters() if read else None
+        _check(lib().ptb_device_counters(self._h, cumulative, C.byref(ctr) if ctr is not None else None))
+        return ctr.as_dict() if ctr is not None else None
+
     def buffer(self, nbytes):
         return Buffer(self, nbytes)
 
@@ -504,6 +512,20 @@ class Buffer:
         _check(lib().ptb_buffer_read(self._h, _p(out), out.nbytes, offset))
         self.dev.sync()
         return out
+
+    def write_async(self, arr, offset=0):
+        """H2D on the device's stream without waiting; `arr` (page-locked for a truly asynchronous copy) must stay alive
+        and unchanged until the device is synchronised."""
+        _check(lib().ptb_buffer_write(self._h, _p(arr), arr.nbytes, offset))
+
+    def read_async(self, out, offset=0):
+        """D2H on the device's stream into `out` (a numpy array, page-locked for a truly asynchronous copy); valid after
+        the device is synchronised."""
+        _check(lib().ptb_buffer_read(self._h, _p(out), out.nbytes, offset))
+
+    def to_rgb8(self, n_pixels, rgb):
+        """the reference's output transform on the device: this float4 frame -> 3 bytes per pixel in `rgb` (a Buffer)"""
+        _check(lib().ptb_buffer_to_rgb8(self._h, n_pixels, rgb._h))
 
     def clear(self):
         _check(lib().ptb_buffer_clear(self._h))

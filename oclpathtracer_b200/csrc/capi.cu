@@ -70,6 +70,8 @@ struct ptb_device {
     } slots[2];
     uint64_t jobs_submitted = 0;
     int tune[16] = {0};  // experiment knobs (ptb_device_set_tuning)
+    bool cumulative_counters = false;  // ptb_device_counters: do not clear the counters per render call
+    uint64_t cumulative_samples = 0;
     // measurement
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;   // triples: before integrator, after integrator, after resolve
@@ -735,7 +737,8 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
     else if (int rc = ensure(&dev->samples, &dev->samples_bytes, size_t(fpb) * n_local * 16)) return rc;
     if (p->accum == PTB_ACCUM_LINEAR)
         if (int rc = ensure(&dev->sum, &dev->sum_bytes, size_t(n_local) * 16)) return rc;
-    CU_TRY(cudaMemsetAsync(dev->counters, 0, sizeof(unsigned long long) * 64, dev->stream));
+    if (!dev->cumulative_counters) CU_TRY(cudaMemsetAsync(dev->counters, 0, sizeof(unsigned long long) * 64, dev->stream));
+    else if (phase != PHASE_RESOLVE) dev->cumulative_samples += (uint64_t)n_local * (uint64_t)p->n_frames;
 
     ptd::RenderArgs a;
     std::memset(&a, 0, sizeof a);
@@ -1293,6 +1296,44 @@ extern "C" int ptb_launch_deserialize(ptb_device* dev, const char* path, ptb_buf
 extern "C" int ptb_device_set_tuning(ptb_device* dev, int index, int value) {
     if (!dev || index < 0 || index >= 16) return fail(PTB_E_INVALID, "ptb_device_set_tuning: bad arguments");
     dev->tune[index] = value;
+    return PTB_OK;
+}
+
+extern "C" int ptb_device_counters(ptb_device* dev, int cumulative, ptb_counters* out) {
+    if (!dev) return fail(PTB_E_INVALID, "ptb_device_counters: null device");
+    if (set_device(dev)) return PTB_E_CUDA;
+    if (out) {
+        unsigned long long h[ptd::CTR_COUNT];
+        CU_TRY(cudaMemcpyAsync(h, dev->counters, sizeof h, cudaMemcpyDeviceToHost, dev->stream));
+        CU_TRY(cudaMemsetAsync(dev->counters, 0, sizeof(unsigned long long) * ptd::CTR_COUNT, dev->stream));
+        CU_TRY(cudaStreamSynchronize(dev->stream));
+        std::memset(out, 0, sizeof *out);
+        out->rays_closest = h[ptd::CTR_CLOSEST]; out->rays_any = h[ptd::CTR_ANY];
+        out->nodes = h[ptd::CTR_NODES]; out->tri_tests = h[ptd::CTR_TESTS];
+        out->samples = dev->cumulative_samples;
+        dev->cumulative_samples = 0;
+    }
+    if (cumulative >= 0) {
+        if ((cumulative != 0) != dev->cumulative_counters) {
+            CU_TRY(cudaMemsetAsync(dev->counters, 0, sizeof(unsigned long long) * ptd::CTR_COUNT, dev->stream));
+            dev->cumulative_samples = 0;
+        }
+        dev->cumulative_counters = cumulative != 0;
+    }
+    return PTB_OK;
+}
+
+extern "C" int ptb_buffer_to_rgb8(ptb_buffer* frame, int n_pixels, ptb_buffer* rgb) {
+    if (!frame || !rgb || n_pixels < 0) return fail(PTB_E_INVALID, "ptb_buffer_to_rgb8: bad arguments");
+    if (size_t(n_pixels) * 16 > frame->bytes || size_t(n_pixels) * 3 > rgb->bytes) return fail(PTB_E_INVALID, "ptb_buffer_to_rgb8: buffer too small");
+    if ((reinterpret_cast<uintptr_t>(rgb->d_ptr) & 15u) != 0) return fail(PTB_E_INVALID, "ptb_buffer_to_rgb8: rgb must be 16-byte aligned");
+    if (n_pixels == 0) return PTB_OK;
+    ptb_device* dev = frame->dev;
+    if (set_device(dev)) return PTB_E_CUDA;
+    ptd::k_to_rgb8<<<((n_pixels + 3) / 4 + 255) / 256, 256, 0, dev->stream>>>(static_cast<const float4*>(frame->d_ptr), n_pixels,
+                                                                              static_cast<uint8_t*>(rgb->d_ptr));
+    CU_TRY(cudaGetLastError());
+    dev->kernel_launches += 1;
     return PTB_OK;
 }
 

@@ -303,16 +303,18 @@ def test_bench_reference_arm_runs_without_gpu():
     import subprocess
     import sys
     from conftest import ROOT
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "c2"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["value"] > 0 and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("c2")
+    import bench
+    assert d["config"] == bench.config_of("c2", 1)  # the same `config` as this repo's arm prints for that workload
 
 
 def test_bench_refuses_without_gpu():
@@ -350,9 +352,14 @@ def test_bench_reference_arm_under_torchrun():
     import sys
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29641", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
-                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+                        "--warmup", "0"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the arm must still use every host core it may run on
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert len(os.sched_getaffinity(0)) == 1 or d["cpu_baseline"]["cores"] > 1
+    import bench
+    assert d["config"] == bench.config_of("c5", 2) and d["config"]["workload"].startswith("c5")  # default workload, same config as our arm
