@@ -74,6 +74,10 @@ int ptb_buffer_map(ptb_buffer* buf, void** host_ptr);
 int ptb_buffer_unmap(ptb_buffer* buf, void* host_ptr);
 int ptb_buffer_clear(ptb_buffer* buf); /* Buffer<T>::clear  Adl/Adl.h:226 */
 void* ptb_buffer_device_ptr(ptb_buffer* buf);
+/* ptb_launch1d keys its resident scene and its frame-ahead batch on the buffers' contents as written through THIS API
+ * (write / unmap / clear).  A tBuffer or matBuffer rewritten behind its back -- by a kernel or copy using
+ * ptb_buffer_device_ptr, or by an IPC peer -- must be marked, or the old scene keeps rendering.                   */
+int ptb_buffer_mark_dirty(ptb_buffer* buf);
 size_t ptb_buffer_size(ptb_buffer* buf);
 
 /* ---- kernel + launcher -----------------------------------------------------------
@@ -208,9 +212,14 @@ int ptb_render_host(ptb_device* dev, const ptb_triangle* tris, int n_tris, const
  * local pixel instead of 16 -- the image a PPM writer needs, at a fifth of the PCIe traffic.
  *
  * Pipelined form: _async enqueues H2D + render + D2H and returns; ptb_job_wait blocks until that job's
- * frame (and stats) are in the caller's buffers and releases the job.  At most two jobs may be in flight
- * (double buffering: job j's D2H overlaps job j+1's render).  Buffers from ptb_host_alloc are pinned, so the
- * copies go straight to / from them; pageable buffers are staged.  Counters are not available here.      */
+ * frame (and stats) are in the caller's buffers and releases the job (waiting twice for one job is an error).  At
+ * most two jobs may be in flight (double buffering: job j's D2H overlaps job j+1's render).  Buffers from
+ * ptb_host_alloc are pinned, so the copies go straight to / from them; pageable buffers are staged.  Counters are
+ * not available here.
+ * Accumulation across calls: accum = LINEAR carries nothing (every call returns the mean of ITS frames).  accum =
+ * REFERENCE with first_frame > 0 continues the gamma-space running mean from the caller's out_rgba, which is read at
+ * SUBMIT time -- so such a call is refused while another job is in flight (wait for it first): the reference's
+ * progressive loop is sequential by definition (GenerateColors.cl:318-321).                                     */
 typedef struct ptb_job ptb_job;
 int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats, int n_mats,
                           const ptb_render_params* params, float* out_rgba, ptb_pixel_stats* out_stats,
@@ -218,6 +227,24 @@ int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, int n_tris,
 int ptb_job_wait(ptb_job* job);
 int ptb_host_alloc(size_t bytes, void** out); /* page-locked host memory */
 int ptb_host_free(void* p);
+
+/* ---- several GPUs in one process (BUILD-DEFINED; the reference picks ONE device, Adl/CL/AdlCL.cpp:154) --------------
+ * ptb_device_add_helper gives `dev` another device of the box that renders part of its work; peer access helper -> dev is
+ * enabled (NVLink / NVSwitch).  Results never change: pixels are independent and a sample depends on (scene, W, H, pixel,
+ * frame) only (GenerateColors.cl:305-308).  From then on
+ *   - ptb_launch1d(dev, ...) deals the frames of its frame-ahead batch over dev and its helpers (each traces into its
+ *     slice of the batch on dev through peer memory), so the unmodified RayCast loop uses every GPU;
+ *   - ptb_render_multi shards ONE image over dev and its helpers (64-pixel blocks round-robin); every device's resolve
+ *     kernel stores its pixels at their global position in the image on dev, which is then read back once.
+ * One host thread drives all devices (asynchronous launches ordered with events).  A helper serves one device; destroy
+ * helpers before or after their device in any order.                                                            */
+int ptb_device_add_helper(ptb_device* dev, ptb_device* helper);
+int ptb_device_helper_count(ptb_device* dev);
+/* HOST buffers in, ONE host image out: out_rgba receives float4 per pixel of the whole image (or 3 bytes per pixel with
+ * params->output = PTB_OUTPUT_RGB8); in/out for accum = REFERENCE with first_frame > 0.  params->shard_* must be unset.
+ * Bit-identical to ptb_render_host on one device.  Synchronises.                                                */
+int ptb_render_multi(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats, int n_mats,
+                     const ptb_render_params* params, float* out_rgba, ptb_counters* counters);
 
 /* ---- measurement hooks ----------------------------------------------------------------
  * (the reference's analogue: Device::toggleProfiling + the ms launch1D returns,

@@ -93,14 +93,14 @@ EXPORTS = [
     "ptb_last_error", "ptb_version", "ptb_device_count", "ptb_device_create", "ptb_device_create_on_stream",
     "ptb_device_destroy", "ptb_device_sync", "ptb_device_name", "ptb_device_sm_count", "ptb_device_memory", "ptb_device_stream",
     "ptb_buffer_create", "ptb_buffer_wrap", "ptb_buffer_destroy", "ptb_buffer_write", "ptb_buffer_read",
-    "ptb_buffer_map", "ptb_buffer_unmap", "ptb_buffer_clear", "ptb_buffer_device_ptr", "ptb_buffer_size",
+    "ptb_buffer_map", "ptb_buffer_unmap", "ptb_buffer_clear", "ptb_buffer_device_ptr", "ptb_buffer_mark_dirty", "ptb_buffer_size",
     "ptb_kernel_get", "ptb_kernel_set_int", "ptb_launch1d", "ptb_launch_serialize", "ptb_launch_deserialize", "ptb_load_model", "ptb_tessellate",
     "ptb_light_from_quad", "ptb_free", "ptb_to_rgb8", "ptb_write_ppm", "ptb_bvh_params_default",
     "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_create_gpu", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_bvh_width", "ptb_scene_mode_width", "ptb_scene_copy_bvh",
     "ptb_render_params_default", "ptb_render_local_pixels", "ptb_render", "ptb_render_host",
     "ptb_buffer_ipc_export", "ptb_buffer_ipc_import", "ptb_render_gather",
     "ptb_render_host_async", "ptb_job_wait", "ptb_host_alloc", "ptb_host_free", "ptb_trace",
-    "ptb_device_profile", "ptb_device_counters", "ptb_buffer_to_rgb8", "ptb_device_profile_read", "ptb_device_set_tuning", "ptb_test_sincos", "ptb_test_pow", "ptb_test_ieee", "ptb_test_rng", "ptb_test_camera",
+    "ptb_device_add_helper", "ptb_device_helper_count", "ptb_render_multi", "ptb_device_profile", "ptb_device_counters", "ptb_buffer_to_rgb8", "ptb_device_profile_read", "ptb_device_set_tuning", "ptb_test_sincos", "ptb_test_pow", "ptb_test_ieee", "ptb_test_rng", "ptb_test_camera",
 ]
 
 
@@ -128,6 +128,7 @@ def lib():
         L.ptb_buffer_destroy.argtypes = [C.c_void_p]
         L.ptb_buffer_clear.argtypes = [C.c_void_p]
         L.ptb_buffer_device_ptr.argtypes = [C.c_void_p]
+        L.ptb_buffer_mark_dirty.argtypes = [C.c_void_p]
         L.ptb_buffer_size.argtypes = [C.c_void_p]
         L.ptb_device_create.argtypes = [C.c_int, C.c_void_p]
         L.ptb_device_create_on_stream.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
@@ -141,6 +142,9 @@ def lib():
         L.ptb_scene_bvh_width.argtypes = [C.c_void_p]
         L.ptb_scene_mode_width.argtypes = [C.c_void_p, C.c_int]
         L.ptb_device_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ptb_device_add_helper.argtypes = [C.c_void_p, C.c_void_p]
+        L.ptb_device_helper_count.argtypes = [C.c_void_p]
+        L.ptb_render_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ptb_buffer_to_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ptb_scene_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptb_scene_create_gpu.argtypes = L.ptb_scene_create.argtypes
@@ -393,6 +397,25 @@ class Device:
                                      _p(stats), C.byref(ctr) if ctr is not None else None))
         return out, stats, (ctr.as_dict() if ctr is not None else None)
 
+    def add_helper(self, helper):
+        """ptb_device_add_helper: `helper` (another Device) renders part of this device's work from now on"""
+        _check(lib().ptb_device_add_helper(self._h, helper._h))
+
+    def helper_count(self):
+        return lib().ptb_device_helper_count(self._h)
+
+    def render_multi(self, tris, mats, params, out=None, want_counters=True):
+        """ptb_render_multi: ONE image sharded over this device and its helpers; host records in, host image out"""
+        n = params.width * params.height
+        if out is None:
+            out = np.zeros((n, 3), np.uint8) if params.output == OUTPUT_RGB8 else np.zeros((n, 4), np.float32)
+        ctr = Counters() if want_counters else None
+        tris = np.ascontiguousarray(tris)
+        mats = np.ascontiguousarray(mats)
+        _check(lib().ptb_render_multi(self._h, _p(tris), len(tris), _p(mats), len(mats), C.byref(params), _p(out),
+                                      C.byref(ctr) if ctr is not None else None))
+        return out, (ctr.as_dict() if ctr is not None else None)
+
     def render_host_async(self, tris, mats, params, out, stats=None):
         """Returns a job handle; call job_wait(handle) before reading `out`.  At most two in flight."""
         job = C.c_void_p()
@@ -538,6 +561,10 @@ class Buffer:
 
     def device_ptr(self):
         return lib().ptb_buffer_device_ptr(self._h)
+
+    def mark_dirty(self):
+        """the contents were changed behind the API's back (a kernel writing through device_ptr()): ptb_launch1d must re-read them"""
+        _check(lib().ptb_buffer_mark_dirty(self._h))
 
     def close(self):
         if self._h:

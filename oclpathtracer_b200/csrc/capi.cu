@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -64,12 +65,20 @@ struct ptb_device {
         void* pin = nullptr; size_t pin_bytes = 0;    // staging when the caller's buffers are pageable
         cudaEvent_t ev_render = nullptr, ev_done = nullptr, ev_up = nullptr;
         bool busy = false;
+        uint64_t serial = 0;
         float* out = nullptr; ptb_pixel_stats* out_stats = nullptr;
         size_t fb = 0, sb = 0;
         bool direct_frame = false, direct_stats = false;
     } slots[2];
     uint64_t jobs_submitted = 0;
     int tune[16] = {0};  // experiment knobs (ptb_device_set_tuning)
+    // helpers: other devices that render part of this device's work (ptb_device_add_helper); their peer access to this device is on
+    std::vector<ptb_device*> helpers;
+    ptb_device* helper_of = nullptr;
+    cudaEvent_t ev_multi = nullptr;                 // cross-device ordering
+    ptb_buffer* multi_frame = nullptr;              // ptb_render_multi: the ONE image (on this device)
+    ptb_buffer* multi_rgb8 = nullptr;
+    void* multi_pin = nullptr; size_t multi_pin_bytes = 0;
     bool cumulative_counters = false;  // ptb_device_counters: do not clear the counters per render call
     uint64_t cumulative_samples = 0;
     // measurement
@@ -107,11 +116,14 @@ struct ptb_kernel {
     int ahead_cfg[3] = {0, 0, 0};
     int last_frame = -2, streak = 0;
     int frame_ahead = 1;  // ptb_kernel_set_int(k, "FRAME_AHEAD", 0) restores one integrator launch per ptb_launch1d
+    std::vector<ptb_scene*> helper_scenes;  // the same scene resident on the device's helpers (frame-ahead batches are dealt over them)
 };
 
 struct ptb_scene {
     ptb_device* dev = nullptr;
-    BuiltBvh bvh;
+    std::shared_ptr<BuiltBvh> bvhp = std::make_shared<BuiltBvh>();  // shared by the per-device copies of one scene (ptb_render_multi)
+    BuiltBvh& built() { return *bvhp; }
+    const BuiltBvh& built() const { return *bvhp; }
     int n_tris = 0, n_mats = 0;
     float4* d_nodes = nullptr;
     float4* d_nodes4 = nullptr;           // FLAT scenes also keep their 4-wide tree resident: coherent-ray modes use it (mode_class)
@@ -124,7 +136,8 @@ struct ptb_scene {
     int n_nodes = 0, depth = 0, bfs_nodes = 0;
     int* d_order = nullptr;               // GPU-built scenes: BVH position -> caller index (device)
     bool host_copy_valid = true;          // false until a GPU-built tree has been downloaded
-    std::vector<ptb_triangle> host_tris;  // kept for the default light lookup
+    std::vector<ptb_triangle> host_tris;  // kept for the default light lookup and for copies of the scene on helper devices
+    std::vector<ptb_material> host_mats;
 };
 
 static int set_device(ptb_device* dev) {
@@ -214,6 +227,24 @@ extern "C" int ptb_device_destroy(ptb_device* dev) {
     if (dev->copy_stream) cudaStreamSynchronize(dev->copy_stream);
     if (dev->up_stream) cudaStreamSynchronize(dev->up_stream);
     if (dev->host_scene) ptb_scene_destroy(dev->host_scene);
+    for (ptb_device* h : dev->helpers) if (h) h->helper_of = nullptr;
+    if (dev->helper_of) {  // scenes that the main device's kernels keep resident here die with this device
+        auto& v = dev->helper_of->helpers;
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (v[i] != dev) continue;
+            for (auto& kv : dev->helper_of->kernels)
+                if (kv.second->helper_scenes.size() > i && kv.second->helper_scenes[i]) {
+                    ptb_scene_destroy(kv.second->helper_scenes[i]);
+                    kv.second->helper_scenes[i] = nullptr;
+                }
+            v[i] = nullptr;
+        }
+        set_device(dev);
+    }
+    if (dev->multi_frame) ptb_buffer_destroy(dev->multi_frame);
+    if (dev->multi_rgb8) ptb_buffer_destroy(dev->multi_rgb8);
+    if (dev->multi_pin) cudaFreeHost(dev->multi_pin);
+    if (dev->ev_multi) cudaEventDestroy(dev->ev_multi);
     for (auto& sl : dev->slots) {
         if (sl.frame) ptb_buffer_destroy(sl.frame);
         if (sl.stats) ptb_buffer_destroy(sl.stats);
@@ -229,7 +260,8 @@ extern "C" int ptb_device_destroy(ptb_device* dev) {
         if (b) ptb_buffer_destroy(b);
     for (auto& kv : dev->kernels) {
         if (kv.second->scene) ptb_scene_destroy(kv.second->scene);
-        if (kv.second->ahead) cudaFree(kv.second->ahead);
+        for (ptb_scene* hs : kv.second->helper_scenes) if (hs) ptb_scene_destroy(hs);
+        if (kv.second->ahead) { set_device(dev); cudaFree(kv.second->ahead); }
         delete kv.second;
     }
     if (dev->samples) cudaFree(dev->samples);
@@ -314,7 +346,7 @@ extern "C" int ptb_buffer_destroy(ptb_buffer* buf) {
 
 extern "C" int ptb_buffer_write(ptb_buffer* buf, const void* host_src, size_t bytes, size_t dst_offset) {
     if (!buf || !host_src) return fail(PTB_E_INVALID, "ptb_buffer_write: null argument");
-    if (dst_offset + bytes > buf->bytes) return fail(PTB_E_INVALID, "ptb_buffer_write: range exceeds buffer");
+    if (bytes > buf->bytes || dst_offset > buf->bytes - bytes) return fail(PTB_E_INVALID, "ptb_buffer_write: range exceeds buffer");
     if (set_device(buf->dev)) return PTB_E_CUDA;
     CU_TRY(cudaMemcpyAsync((char*)buf->d_ptr + dst_offset, host_src, bytes, cudaMemcpyHostToDevice, buf->dev->stream));
     buf->version++;
@@ -323,7 +355,7 @@ extern "C" int ptb_buffer_write(ptb_buffer* buf, const void* host_src, size_t by
 
 extern "C" int ptb_buffer_read(ptb_buffer* buf, void* host_dst, size_t bytes, size_t src_offset) {
     if (!buf || !host_dst) return fail(PTB_E_INVALID, "ptb_buffer_read: null argument");
-    if (src_offset + bytes > buf->bytes) return fail(PTB_E_INVALID, "ptb_buffer_read: range exceeds buffer");
+    if (bytes > buf->bytes || src_offset > buf->bytes - bytes) return fail(PTB_E_INVALID, "ptb_buffer_read: range exceeds buffer");
     if (set_device(buf->dev)) return PTB_E_CUDA;
     CU_TRY(cudaMemcpyAsync(host_dst, (const char*)buf->d_ptr + src_offset, bytes, cudaMemcpyDeviceToHost, buf->dev->stream));
     return PTB_OK;
@@ -356,6 +388,11 @@ extern "C" int ptb_buffer_clear(ptb_buffer* buf) {
 }
 
 extern "C" void* ptb_buffer_device_ptr(ptb_buffer* buf) { return buf ? buf->d_ptr : nullptr; }
+extern "C" int ptb_buffer_mark_dirty(ptb_buffer* buf) {
+    if (!buf) return fail(PTB_E_INVALID, "ptb_buffer_mark_dirty: null");
+    buf->version++;
+    return PTB_OK;
+}
 extern "C" size_t ptb_buffer_size(ptb_buffer* buf) { return buf ? buf->bytes : 0; }
 
 // ---- resident scene ---------------------------------------------------------------------------------
@@ -370,8 +407,9 @@ extern "C" int ptb_scene_destroy(ptb_scene* s) {
     return PTB_OK;
 }
 
-extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats,
-                                int n_mats, const ptb_bvh_params* bvh_params, ptb_scene** out) {
+// `share`: a scene of the SAME records on another device whose host-built tree is reused (one build, one upload per device)
+static int scene_create_impl(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats, int n_mats,
+                             const ptb_bvh_params* bvh_params, const ptb_scene* share, ptb_scene** out) {
     if (!dev || !tris || !mats || !out || n_tris < 1 || n_mats < 1)
         return fail(PTB_E_INVALID, "ptb_scene_create: bad arguments");
     *out = nullptr;
@@ -382,9 +420,12 @@ extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n
     if (bvh_params) bp = *bvh_params; else ptb_bvh_params_default(&bp);
     ptb_scene* s = new ptb_scene();
     s->dev = dev; s->n_tris = n_tris; s->n_mats = n_mats;
-    int rc = build_bvh(tris, n_tris, bp, &s->bvh);
+    int rc = PTB_OK;
+    if (share && share->host_copy_valid) s->bvhp = share->bvhp;
+    else rc = build_bvh(tris, n_tris, bp, &s->built());
     if (rc) { delete s; return rc; }
     s->host_tris.assign(tris, tris + n_tris);
+    s->host_mats.assign(mats, mats + n_mats);
     std::vector<ptb_bvh_tri> orig;
     make_edge_tris(tris, n_tris, &orig);
     std::vector<float4> m(size_t(n_mats) * 2);
@@ -395,9 +436,9 @@ extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n
         m[2 * i + 1] = make_float4(mats[i].emissive.x, mats[i].emissive.y, mats[i].emissive.z, tbits);
     }
     // scene class: everything (4-wide nodes, triangles, materials) fits a 32 KB shared-memory budget -> SMALL
-    const size_t staged4 = s->bvh.nodes4.size() * sizeof(ptb_bvh_node4) + size_t(n_tris) * 48 + size_t(n_mats) * 32;
-    const bool can4 = !s->bvh.nodes4.empty() && staged4 <= 32 * 1024 && int(s->bvh.nodes4.size()) == s->bvh.smem_nodes4;
-    const bool can_flat = !s->bvh.flat.empty();  // <= 32 leaves and <= 64 triangles: no tree, leaf boxes as kernel parameters
+    const size_t staged4 = s->built().nodes4.size() * sizeof(ptb_bvh_node4) + size_t(n_tris) * 48 + size_t(n_mats) * 32;
+    const bool can4 = !s->built().nodes4.empty() && staged4 <= 32 * 1024 && int(s->built().nodes4.size()) == s->built().smem_nodes4;
+    const bool can_flat = !s->built().flat.empty();  // <= 32 leaves and <= 64 triangles: no tree, leaf boxes as kernel parameters
     if ((bp.force_width == 1 && !can_flat) || (bp.force_width == 4 && !can4) || (bp.force_width != 0 && bp.force_width != 1 && bp.force_width != 2 && bp.force_width != 4)) {
         delete s;
         return fail(PTB_E_INVALID, "ptb_scene_create: the scene does not qualify for force_width = %d", bp.force_width);
@@ -405,30 +446,38 @@ extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n
     s->cls = bp.force_width == 1 ? ptd::PTD_FLAT : bp.force_width == 4 ? ptd::PTD_SMALL4 : bp.force_width == 2 ? ptd::PTD_LARGE
              : can_flat ? ptd::PTD_FLAT : can4 ? ptd::PTD_SMALL4 : ptd::PTD_LARGE;
     s->small = s->cls != ptd::PTD_LARGE;
-    if (s->cls == ptd::PTD_FLAT) { s->width = 1; s->n_nodes = int(s->bvh.flat.size()); s->depth = 1; s->bfs_nodes = s->n_nodes; }
-    else if (s->cls == ptd::PTD_SMALL4) { s->width = 4; s->n_nodes = int(s->bvh.nodes4.size()); s->depth = s->bvh.depth4; s->bfs_nodes = s->bvh.smem_nodes4; }
-    else { s->width = 2; s->n_nodes = int(s->bvh.nodes.size()); s->depth = s->bvh.depth; s->bfs_nodes = s->bvh.smem_nodes; }
+    if (s->cls == ptd::PTD_FLAT) { s->width = 1; s->n_nodes = int(s->built().flat.size()); s->depth = 1; s->bfs_nodes = s->n_nodes; }
+    else if (s->cls == ptd::PTD_SMALL4) { s->width = 4; s->n_nodes = int(s->built().nodes4.size()); s->depth = s->built().depth4; s->bfs_nodes = s->built().smem_nodes4; }
+    else { s->width = 2; s->n_nodes = int(s->built().nodes.size()); s->depth = s->built().depth; s->bfs_nodes = s->built().smem_nodes; }
     if (set_device(dev)) { delete s; return PTB_E_CUDA; }
     auto up = [&](float4** d, const void* h, size_t bytes) -> int {
         CU_TRY(cudaMalloc((void**)d, bytes));
         CU_TRY(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, dev->stream));
         return PTB_OK;
     };
-    std::vector<ptb_bvh_leafbox> flat_padded = s->bvh.flat;  // staged count is even: pad with a box that never hits
+    std::vector<ptb_bvh_leafbox> flat_padded = s->built().flat;  // staged count is even: pad with a box that never hits
     if (flat_padded.size() & 1) flat_padded.push_back(ptb_bvh_leafbox{{0.f, 0.f, 0.f}, 0u, {-1e30f, -1e30f, -1e30f}, 0u});
     if ((rc = s->cls == ptd::PTD_FLAT     ? up(&s->d_nodes, flat_padded.data(), flat_padded.size() * sizeof(ptb_bvh_leafbox))
-              : s->cls == ptd::PTD_SMALL4 ? up(&s->d_nodes, s->bvh.nodes4.data(), s->bvh.nodes4.size() * sizeof(ptb_bvh_node4))
-                                          : up(&s->d_nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptb_bvh_node))) ||
-        (s->cls == ptd::PTD_FLAT && can4 && bp.force_width == 0 && (rc = up(&s->d_nodes4, s->bvh.nodes4.data(), s->bvh.nodes4.size() * sizeof(ptb_bvh_node4)))) ||
-        (rc = up(&s->d_tris, s->bvh.tris.data(), s->bvh.tris.size() * 48)) ||
+              : s->cls == ptd::PTD_SMALL4 ? up(&s->d_nodes, s->built().nodes4.data(), s->built().nodes4.size() * sizeof(ptb_bvh_node4))
+                                          : up(&s->d_nodes, s->built().nodes.data(), s->built().nodes.size() * sizeof(ptb_bvh_node))) ||
+        (s->cls == ptd::PTD_FLAT && can4 && bp.force_width == 0 && (rc = up(&s->d_nodes4, s->built().nodes4.data(), s->built().nodes4.size() * sizeof(ptb_bvh_node4)))) ||
+        (rc = up(&s->d_tris, s->built().tris.data(), s->built().tris.size() * 48)) ||
         (rc = up(&s->d_tris_orig, orig.data(), orig.size() * 48)) || (rc = up(&s->d_mats, m.data(), m.size() * 16))) {
         ptb_scene_destroy(s);
         return rc;
     }
     // the host vectors `orig` and `m` die at return: finish the copies now
-    CU_TRY(cudaStreamSynchronize(dev->stream));
+    if (cudaError_t e = cudaStreamSynchronize(dev->stream); e != cudaSuccess) {
+        ptb_scene_destroy(s);
+        return fail(PTB_E_CUDA, "ptb_scene_create: upload failed: %s", cudaGetErrorString(e));
+    }
     *out = s;
     return PTB_OK;
+}
+
+extern "C" int ptb_scene_create(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats,
+                                int n_mats, const ptb_bvh_params* bvh_params, ptb_scene** out) {
+    return scene_create_impl(dev, tris, n_tris, mats, n_mats, bvh_params, nullptr, out);
 }
 
 // Scene whose BVH is built on the device (lbvh.cuh).  Only the root is guaranteed to sit at index 0, so one
@@ -498,12 +547,18 @@ extern "C" int ptb_bvh_build_host(const ptb_triangle* tris, int n_tris, const pt
                               : width == 4 ? b.nodes4.size() * sizeof(ptb_bvh_node4) : b.nodes.size() * sizeof(ptb_bvh_node);
     *nodes = std::malloc(node_bytes);
     *tri_order = static_cast<int32_t*>(std::malloc(b.tri_order.size() * sizeof(int32_t)));
-    if (!*nodes || !*tri_order) return fail(PTB_E_NOMEM, "ptb_bvh_build_host: out of memory");
+    if (ordered_tris) *ordered_tris = nullptr;
+    auto oom = [&]() {
+        std::free(*nodes); std::free(*tri_order);
+        *nodes = nullptr; *tri_order = nullptr;
+        return fail(PTB_E_NOMEM, "ptb_bvh_build_host: out of memory");
+    };
+    if (!*nodes || !*tri_order) return oom();
     std::memcpy(*nodes, width == 1 ? (const void*)b.flat.data() : width == 4 ? (const void*)b.nodes4.data() : (const void*)b.nodes.data(), node_bytes);
     std::memcpy(*tri_order, b.tri_order.data(), b.tri_order.size() * sizeof(int32_t));
     if (ordered_tris) {
         *ordered_tris = static_cast<ptb_bvh_tri*>(std::malloc(b.tris.size() * sizeof(ptb_bvh_tri)));
-        if (!*ordered_tris) return fail(PTB_E_NOMEM, "ptb_bvh_build_host: out of memory");
+        if (!*ordered_tris) return oom();
         std::memcpy(*ordered_tris, b.tris.data(), b.tris.size() * sizeof(ptb_bvh_tri));
     }
     *n_nodes = int(width == 1 ? b.flat.size() : width == 4 ? b.nodes4.size() : b.nodes.size());
@@ -527,19 +582,19 @@ extern "C" int ptb_scene_copy_bvh(ptb_scene* s, void* nodes, int32_t* tri_order)
     if (!s) return fail(PTB_E_INVALID, "ptb_scene_copy_bvh: null scene");
     if (!s->host_copy_valid) {  // GPU-built tree: download on first request
         if (set_device(s->dev)) return PTB_E_CUDA;
-        s->bvh.nodes.resize(size_t(s->n_nodes));
-        s->bvh.tri_order.resize(size_t(s->n_tris));
-        CU_TRY(cudaMemcpyAsync(s->bvh.nodes.data(), s->d_nodes, size_t(s->n_nodes) * sizeof(ptb_bvh_node), cudaMemcpyDeviceToHost, s->dev->stream));
-        CU_TRY(cudaMemcpyAsync(s->bvh.tri_order.data(), s->d_order, size_t(s->n_tris) * 4, cudaMemcpyDeviceToHost, s->dev->stream));
+        s->built().nodes.resize(size_t(s->n_nodes));
+        s->built().tri_order.resize(size_t(s->n_tris));
+        CU_TRY(cudaMemcpyAsync(s->built().nodes.data(), s->d_nodes, size_t(s->n_nodes) * sizeof(ptb_bvh_node), cudaMemcpyDeviceToHost, s->dev->stream));
+        CU_TRY(cudaMemcpyAsync(s->built().tri_order.data(), s->d_order, size_t(s->n_tris) * 4, cudaMemcpyDeviceToHost, s->dev->stream));
         CU_TRY(cudaStreamSynchronize(s->dev->stream));
         s->host_copy_valid = true;
     }
     if (nodes) {
-        if (s->width == 1) std::memcpy(nodes, s->bvh.flat.data(), s->bvh.flat.size() * sizeof(ptb_bvh_leafbox));
-        else if (s->width == 4) std::memcpy(nodes, s->bvh.nodes4.data(), s->bvh.nodes4.size() * sizeof(ptb_bvh_node4));
-        else std::memcpy(nodes, s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptb_bvh_node));
+        if (s->width == 1) std::memcpy(nodes, s->built().flat.data(), s->built().flat.size() * sizeof(ptb_bvh_leafbox));
+        else if (s->width == 4) std::memcpy(nodes, s->built().nodes4.data(), s->built().nodes4.size() * sizeof(ptb_bvh_node4));
+        else std::memcpy(nodes, s->built().nodes.data(), s->built().nodes.size() * sizeof(ptb_bvh_node));
     }
-    if (tri_order) std::memcpy(tri_order, s->bvh.tri_order.data(), s->bvh.tri_order.size() * sizeof(int32_t));
+    if (tri_order) std::memcpy(tri_order, s->built().tri_order.data(), s->built().tri_order.size() * sizeof(int32_t));
     return PTB_OK;
 }
 
@@ -563,9 +618,9 @@ static ptd::SceneDev scene_dev(const ptb_scene* s, int cls) {
     d.nodes = s->d_nodes; d.tris = s->d_tris; d.tris_orig = s->d_tris_orig; d.mats = s->d_mats;
     d.n_nodes = s->n_nodes; d.n_tris = s->n_tris; d.n_mats = s->n_mats;
     if (cls == ptd::PTD_SMALL4 && s->cls == ptd::PTD_FLAT) {  // the resident 4-wide tree of a FLAT scene
-        d.nodes = s->d_nodes4; d.n_nodes = int(s->bvh.nodes4.size());
-        d.smem_nodes = s->bvh.smem_nodes4; d.small = 1; d.flat_n = 0; d.lstack = 0; d.ld256 = 0;
-        d.stack_depth = 3 * s->bvh.depth4 + 1;
+        d.nodes = s->d_nodes4; d.n_nodes = int(s->built().nodes4.size());
+        d.smem_nodes = s->built().smem_nodes4; d.small = 1; d.flat_n = 0; d.lstack = 0; d.ld256 = 0;
+        d.stack_depth = 3 * s->built().depth4 + 1;
         return d;
     }
     // Large scenes stage only the top of the tree: a 64-node (4 KB) prefix keeps >= 6 CTAs per SM
@@ -575,7 +630,7 @@ static ptd::SceneDev scene_dev(const ptb_scene* s, int cls) {
     d.small = s->small ? 1 : 0;
     d.flat_n = 0;
     if (s->cls == ptd::PTD_FLAT) {
-        d.flat_n = (int(s->bvh.flat.size()) + 1) & ~1;
+        d.flat_n = (int(s->built().flat.size()) + 1) & ~1;
         d.smem_nodes = 0;
     }
     d.stack_depth = s->width == 4 ? 3 * s->depth + 1 : s->depth + 1;  // a 4-wide visit defers up to three children
@@ -610,7 +665,8 @@ template <int MODE, bool BVH, int SMALL, bool STATS>
 static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::RenderArgs& a) {
     const int block = (a.tune[3] == 64 || a.tune[3] == 32) ? a.tune[3] : 128;
     if (MODE == PTB_MODE_PATH && a.tune[5] == 0) {  // persistent grid with path regeneration (tune[5]=1: one sample per thread)
-        const size_t smem = ptd::scene_smem_bytes(sc, BVH, SMALL, block);
+        // tune[9] = extra KB of (unused) shared memory per CTA: lowers the occupancy for latency-sensitivity measurements
+        const size_t smem = ptd::scene_smem_bytes(sc, BVH, SMALL, block) + (a.tune[9] > 0 ? size_t(a.tune[9]) * 1024 : 0);
         auto k = ptd::k_mega_path_regen<BVH, SMALL, STATS>;
         int per_sm = 0;
         if (int rc = set_smem(k, smem, block, &per_sm)) return rc;
@@ -766,6 +822,11 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
     }
     a.shard.index = p->shard_index; a.shard.count = p->shard_count < 1 ? 1 : p->shard_count; a.shard.block = p->shard_block < 1 ? 1 : p->shard_block;
     a.samples = ext_samples ? ext_samples : static_cast<float4*>(dev->samples);
+    // One frame with accum = LINEAR: the mean of one sample is the sample (0 + c = c and c / 1 = c exactly, w = 1), and without image
+    // sharding a pixel's slot in the batch IS its place in the frame -- the integrator writes the frame itself and the resolve
+    // launch is dropped (C1: one launch instead of two on a 30 us step).  Bit-identical by construction.
+    const bool direct = phase == PHASE_BOTH && !ext_samples && p->accum == PTB_ACCUM_LINEAR && p->n_frames == 1 && p->shard_count <= 1 && n_peers <= 0;
+    if (direct) a.samples = d_frame;
     a.stats = stats ? d_stats : nullptr;
     a.stats_frame = p->first_frame + p->n_frames - 1;
     a.counters = dev->counters;
@@ -806,6 +867,10 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
         if (ev) CU_TRY(cudaEventRecord(ev[1], dev->stream));
         if (phase != PHASE_RESOLVE) dev->integrator_launch_batches++;
         if (phase == PHASE_TRACE) continue;
+        if (direct) {
+            if (ev) CU_TRY(cudaEventRecord(ev[2], dev->stream));
+            continue;
+        }
         ptd::ResolveArgs r;
         r.samples = a.samples; r.n_local = n_local; r.frames_in_batch = nb; r.first_frame = a.first_frame;
         r.accum = p->accum; r.first_batch = f0 == 0; r.last_batch = f0 + nb >= p->n_frames;
@@ -936,7 +1001,11 @@ extern "C" int ptb_job_wait(ptb_job* job) {
     ptb_device* dev = job->dev;
     auto& sl = dev->slots[job->slot];
     int rc = PTB_OK;
-    if (sl.busy) {
+    if (!sl.busy || sl.serial != job->serial) {  // a handle that was already waited for (the slot may serve a newer job by now)
+        delete job;
+        return fail(PTB_E_INVALID, "ptb_job_wait: this job has already been waited for");
+    }
+    {
         if (set_device(dev)) rc = PTB_E_CUDA;
         cudaError_t e = cudaEventSynchronize(sl.ev_done);
         if (e != cudaSuccess) rc = fail(PTB_E_CUDA, "ptb_job_wait: %s", cudaGetErrorString(e));
@@ -966,11 +1035,18 @@ extern "C" int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, 
     const bool rgb8 = params->output == PTB_OUTPUT_RGB8;
     if (rgb8 && params->accum == PTB_ACCUM_REFERENCE && params->first_frame > 0)
         return fail(PTB_E_INVALID, "ptb_render_host: RGB8 output cannot carry the gamma-space state of accum=REFERENCE across calls "
-                                   "(first_frame > 0); use FLOAT4 output or accum=LINEAR");
+                                   "(first_frame > 0); use FLOAT4 output (accum=LINEAR carries nothing across calls: it is the mean of this call's frames)");
     const size_t cb = rgb8 ? size_t(n_local) * 3 : fb;  // bytes of the image that travel to the host
-    const int si = int(dev->jobs_submitted & 1);
+    const int si = !dev->slots[0].busy ? 0 : (!dev->slots[1].busy ? 1 : -1);  // any free slot
+    if (si < 0) return fail(PTB_E_INVALID, "ptb_render_host_async: two jobs are in flight; wait for one first");
     auto& sl = dev->slots[si];
-    if (sl.busy) return fail(PTB_E_INVALID, "ptb_render_host_async: more than two jobs in flight; wait for the older one first");
+    // The gamma-space running mean of accum=REFERENCE continues from the caller's out_rgba, which is uploaded NOW: with a job still
+    // in flight that state may not have reached the host yet (its D2H is asynchronous, pageable buffers land at ptb_job_wait), and
+    // the frames in between would silently drop out of the mean.  A progressive REFERENCE loop is sequential by its definition
+    // (GenerateColors.cl:318-321 reads the previous frame's gDst): wait for the previous job first.
+    if (params->accum == PTB_ACCUM_REFERENCE && params->first_frame > 0 && (dev->slots[0].busy || dev->slots[1].busy))
+        return fail(PTB_E_INVALID, "ptb_render_host_async: accum=REFERENCE with first_frame > 0 continues from out_rgba; "
+                                   "wait for the job in flight before submitting the next frame range");
     int rc;
     if (!dev->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
     if (!dev->up_stream) CU_TRY(cudaStreamCreateWithFlags(&dev->up_stream, cudaStreamNonBlocking));
@@ -1050,7 +1126,7 @@ extern "C" int ptb_render_host_async(ptb_device* dev, const ptb_triangle* tris, 
     if (sb) CU_TRY(cudaMemcpyAsync(sl.direct_stats ? (void*)out_stats : (void*)(pin + cb), sl.stats->d_ptr, sb, cudaMemcpyDeviceToHost, dev->copy_stream));
     CU_TRY(cudaStreamWaitEvent(dev->copy_stream, sl.ev_up, 0));
     CU_TRY(cudaEventRecord(sl.ev_done, dev->copy_stream));
-    sl.busy = true; sl.out = out_rgba; sl.out_stats = out_stats; sl.fb = cb; sl.sb = sb;
+    sl.busy = true; sl.serial = dev->jobs_submitted; sl.out = out_rgba; sl.out_stats = out_stats; sl.fb = cb; sl.sb = sb;
     ptb_job* job = new ptb_job{dev, si, dev->jobs_submitted};
     dev->jobs_submitted++;
     *job_out = job;
@@ -1076,6 +1152,130 @@ extern "C" int ptb_render_host(ptb_device* dev, const ptb_triangle* tris, int n_
         counters->rays_closest = hc[ptd::CTR_CLOSEST]; counters->rays_any = hc[ptd::CTR_ANY];
         counters->nodes = hc[ptd::CTR_NODES]; counters->tri_tests = hc[ptd::CTR_TESTS];
         counters->samples = (uint64_t)ptb_render_local_pixels(params) * (uint64_t)params->n_frames;
+    }
+    return PTB_OK;
+}
+
+// ---- several GPUs in one process (BUILD-DEFINED; the reference is single-device: Adl/CL/AdlCL.cpp:154 picks ONE) ---------
+// A device can be given HELPERS: other devices of the box that render part of its work.  Pixels are independent and a
+// sample depends on (scene, W, H, pixel, frame) only (GenerateColors.cl:305-308), so the work is dealt without changing a
+// bit of the result: ptb_render_multi shards the image (64-pixel blocks round-robin) and every device's resolve kernel stores
+// its pixels straight into the ONE image on the main device over NVLink peer memory; ptb_launch1d deals the frames of its
+// frame-ahead batch.  One host thread: work is enqueued asynchronously on each device's own stream and ordered with events.
+
+static int ensure_event(ptb_device* d) {
+    if (d->ev_multi) return PTB_OK;
+    if (set_device(d)) return PTB_E_CUDA;
+    CU_TRY(cudaEventCreateWithFlags(&d->ev_multi, cudaEventDisableTiming));
+    return PTB_OK;
+}
+
+extern "C" int ptb_device_add_helper(ptb_device* dev, ptb_device* helper) {
+    if (!dev || !helper || dev == helper) return fail(PTB_E_INVALID, "ptb_device_add_helper: bad arguments");
+    if (helper->helper_of || !helper->helpers.empty() || dev->helper_of) return fail(PTB_E_INVALID, "ptb_device_add_helper: a helper serves one device and has no helpers of its own");
+    if (int(dev->helpers.size()) >= PTB_MAX_PEERS) return fail(PTB_E_INVALID, "ptb_device_add_helper: at most %d helpers", PTB_MAX_PEERS);
+    if (helper->index != dev->index) {
+        int can = 0;
+        CU_TRY(cudaDeviceCanAccessPeer(&can, helper->index, dev->index));
+        if (!can) return fail(PTB_E_CUDA, "ptb_device_add_helper: device %d cannot access the memory of device %d", helper->index, dev->index);
+        if (set_device(helper)) return PTB_E_CUDA;
+        cudaError_t e = cudaDeviceEnablePeerAccess(dev->index, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(PTB_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    if (int rc = ensure_event(dev)) return rc;
+    if (int rc = ensure_event(helper)) return rc;
+    dev->helpers.push_back(helper);
+    helper->helper_of = dev;
+    return PTB_OK;
+}
+
+extern "C" int ptb_device_helper_count(ptb_device* dev) {
+    int n = 0;
+    if (dev) for (ptb_device* h : dev->helpers) n += h != nullptr;
+    return n;
+}
+
+extern "C" int ptb_render_multi(ptb_device* dev, const ptb_triangle* tris, int n_tris, const ptb_material* mats, int n_mats,
+                                const ptb_render_params* params, float* out_rgba, ptb_counters* counters) {
+    if (!dev || !tris || !mats || !out_rgba) return fail(PTB_E_INVALID, "ptb_render_multi: null argument");
+    if (int rc = validate(params)) return rc;
+    if (params->shard_count > 1) return fail(PTB_E_INVALID, "ptb_render_multi: the call shards the image itself (shard_count must be <= 1)");
+    const bool rgb8 = params->output == PTB_OUTPUT_RGB8;
+    if (rgb8 && params->accum == PTB_ACCUM_REFERENCE && params->first_frame > 0)
+        return fail(PTB_E_INVALID, "ptb_render_multi: RGB8 output cannot carry the gamma-space state of accum=REFERENCE across calls (first_frame > 0)");
+    std::vector<ptb_device*> devs{dev};
+    for (ptb_device* h : dev->helpers) if (h) devs.push_back(h);
+    const int n = int(devs.size());
+    const size_t npix = size_t(params->width) * size_t(params->height);
+    if (npix < size_t(n) * 64) devs.resize(1);  // fewer 64-pixel blocks than devices: one device renders it all
+    const int nd = int(devs.size());
+    // resident copies of the scene: rebuilt only when the records changed; the host-built tree is shared
+    const size_t tb = size_t(n_tris) * sizeof(ptb_triangle), mb = size_t(n_mats) * sizeof(ptb_material);
+    uint64_t h = content_hash(tris, tb, 1469598103934665603ull);
+    h = content_hash(mats, mb, h);
+    const ptb_scene* fresh = nullptr;
+    for (ptb_device* d : devs)
+        if (d->host_scene && d->host_scene_hash == h) { fresh = d->host_scene; break; }
+    for (ptb_device* d : devs) {
+        if (d->host_scene && d->host_scene_hash == h) continue;
+        if (d->host_scene) ptb_scene_destroy(d->host_scene);
+        d->host_scene = nullptr;
+        if (int rc = scene_create_impl(d, tris, n_tris, mats, n_mats, nullptr, fresh, &d->host_scene)) return rc;
+        d->host_scene_hash = h;
+        if (!fresh) fresh = d->host_scene;
+    }
+    int rc;
+    if ((rc = ensure_buffer(dev, &dev->multi_frame, npix * 16)) || (rgb8 && (rc = ensure_buffer(dev, &dev->multi_rgb8, (npix * 3 + 15) & ~size_t(15))))) return rc;
+    if ((rc = ensure_event(dev))) return rc;
+    if (set_device(dev)) return PTB_E_CUDA;
+    if (params->accum == PTB_ACCUM_REFERENCE && params->first_frame > 0) {  // in/out state of the gamma-space running mean
+        if ((rc = ptb_buffer_write(dev->multi_frame, out_rgba, npix * 16, 0))) return rc;
+        CU_TRY(cudaStreamSynchronize(dev->stream));
+    }
+    CU_TRY(cudaEventRecord(dev->ev_multi, dev->stream));
+    float4* image = static_cast<float4*>(dev->multi_frame->d_ptr);
+    for (int j = 0; j < nd; ++j) {
+        ptb_device* d = devs[j];
+        ptb_render_params pj = *params;
+        pj.shard_index = j; pj.shard_count = nd; pj.shard_block = 64;
+        if (d != dev) {
+            if ((rc = ensure_event(d))) return rc;
+            if (set_device(d)) return PTB_E_CUDA;
+            CU_TRY(cudaStreamWaitEvent(d->stream, dev->ev_multi, 0));  // the image (and its state) is ready on the main device
+        }
+        if ((rc = render_impl(d, d->host_scene, &pj, image, npix * 16, nullptr, 0, nullptr, nullptr, PHASE_BOTH, nullptr, 0))) return rc;
+        if (d != dev) CU_TRY(cudaEventRecord(d->ev_multi, d->stream));
+    }
+    if (set_device(dev)) return PTB_E_CUDA;
+    for (int j = 1; j < nd; ++j) CU_TRY(cudaStreamWaitEvent(dev->stream, devs[j]->ev_multi, 0));
+    const size_t cb = rgb8 ? npix * 3 : npix * 16;
+    if (rgb8) {
+        ptd::k_to_rgb8<<<unsigned(((npix + 3) / 4 + 255) / 256), 256, 0, dev->stream>>>(image, int(npix), static_cast<uint8_t*>(dev->multi_rgb8->d_ptr));
+        CU_TRY(cudaGetLastError());
+        dev->kernel_launches += 1;
+    }
+    const bool direct = is_pinned(out_rgba);
+    if (!direct && dev->multi_pin_bytes < cb) {
+        if (dev->multi_pin) cudaFreeHost(dev->multi_pin);
+        dev->multi_pin = nullptr; dev->multi_pin_bytes = 0;
+        CU_TRY(cudaMallocHost(&dev->multi_pin, cb));
+        dev->multi_pin_bytes = cb;
+    }
+    CU_TRY(cudaMemcpyAsync(direct ? (void*)out_rgba : dev->multi_pin, rgb8 ? dev->multi_rgb8->d_ptr : (void*)image, cb, cudaMemcpyDeviceToHost, dev->stream));
+    CU_TRY(cudaStreamSynchronize(dev->stream));
+    if (!direct) std::memcpy(out_rgba, dev->multi_pin, cb);
+    if (counters) {
+        std::memset(counters, 0, sizeof *counters);
+        for (ptb_device* d : devs) {
+            unsigned long long hc[ptd::CTR_COUNT];
+            if (set_device(d)) return PTB_E_CUDA;
+            CU_TRY(cudaMemcpyAsync(hc, d->counters, sizeof hc, cudaMemcpyDeviceToHost, d->stream));
+            CU_TRY(cudaStreamSynchronize(d->stream));
+            counters->rays_closest += hc[ptd::CTR_CLOSEST]; counters->rays_any += hc[ptd::CTR_ANY];
+            counters->nodes += hc[ptd::CTR_NODES]; counters->tri_tests += hc[ptd::CTR_TESTS];
+        }
+        counters->samples = (uint64_t)npix * (uint64_t)params->n_frames;
     }
     return PTB_OK;
 }
@@ -1153,6 +1353,7 @@ extern "C" int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* b
         if (!k->scene || h != k->hash) {
             if (k->scene) ptb_scene_destroy(k->scene);
             k->scene = nullptr;
+            for (ptb_scene*& hs : k->helper_scenes) { if (hs) ptb_scene_destroy(hs); hs = nullptr; }
             if (int rc = ptb_scene_create(dev, ht.data(), nt, hm.data(), nm, nullptr, &k->scene)) return rc;
             k->hash = h;
             scene_rebuilt = true;
@@ -1194,12 +1395,47 @@ extern "C" int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* b
             want = 0;
         }
         if (want >= 2) {
-            ptb_render_params pb = p;
-            pb.n_frames = want;
-            if (int rc = render_impl(dev, k->scene, &pb, nullptr, 0, nullptr, 0, nullptr, static_cast<float4*>(k->ahead), PHASE_TRACE)) {
-                k->ahead_count = 0;
-                return rc;
+            // the frames of the batch are dealt over this device and its helpers (ptb_device_add_helper): each traces its
+            // frames into its slice of the batch on THIS device (stores over NVLink peer memory); the resolves stay here
+            std::vector<ptb_device*> devs{dev};
+            std::vector<ptb_scene*> scs{k->scene};
+            k->helper_scenes.resize(dev->helpers.size(), nullptr);
+            for (size_t i = 0; i < dev->helpers.size() && int(devs.size()) < want; ++i) {
+                ptb_device* hd = dev->helpers[i];
+                if (!hd) continue;
+                if (!k->helper_scenes[i] &&
+                    scene_create_impl(hd, k->scene->host_tris.data(), k->scene->n_tris, k->scene->host_mats.data(), k->scene->n_mats, nullptr,
+                                      k->scene, &k->helper_scenes[i]) != PTB_OK) {
+                    k->helper_scenes[i] = nullptr;
+                    continue;  // this helper cannot hold the scene: the others do the work
+                }
+                devs.push_back(hd); scs.push_back(k->helper_scenes[i]);
             }
+            const int nd = int(devs.size());
+            if (nd > 1) {
+                if (set_device(dev)) return PTB_E_CUDA;
+                CU_TRY(cudaEventRecord(dev->ev_multi, dev->stream));  // the previous batch has been consumed up to here
+            }
+            int off = 0;
+            for (int j = 0; j < nd; ++j) {
+                const int cnt = want / nd + (j < want % nd ? 1 : 0);
+                ptb_render_params pb = p;
+                pb.first_frame = z + off; pb.n_frames = cnt;
+                ptb_device* d = devs[j];
+                if (d != dev) {
+                    if (set_device(d)) return PTB_E_CUDA;
+                    CU_TRY(cudaStreamWaitEvent(d->stream, dev->ev_multi, 0));
+                }
+                int rc = render_impl(d, scs[j], &pb, nullptr, 0, nullptr, 0, nullptr, static_cast<float4*>(k->ahead) + size_t(off) * size_t(n_threads), PHASE_TRACE);
+                if (rc == PTB_OK && d != dev && cudaEventRecord(d->ev_multi, d->stream) != cudaSuccess) rc = fail(PTB_E_CUDA, "ptb_launch1d: cudaEventRecord failed");
+                if (rc) {
+                    k->ahead_count = 0;
+                    return rc;
+                }
+                off += cnt;
+            }
+            if (set_device(dev)) return PTB_E_CUDA;
+            for (int j = 1; j < nd; ++j) CU_TRY(cudaStreamWaitEvent(dev->stream, devs[j]->ev_multi, 0));
             k->ahead_first = z; k->ahead_count = want;
         }
     }

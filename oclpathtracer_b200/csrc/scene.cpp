@@ -185,8 +185,11 @@ extern "C" int ptb_to_rgb8(const float* rgba, int n_pixels, uint8_t* rgb) {
     if (!rgba || !rgb || n_pixels < 0) return ptb::fail(PTB_E_INVALID, "ptb_to_rgb8: bad arguments");
     for (int i = 0; i < n_pixels; ++i)
         for (int c = 0; c < 3; ++c) {
-            float a = std::sqrt(rgba[4 * size_t(i) + c]) * 255.0f;
-            int b = (a == a) ? int(a) : 0;  // (int)NaN is undefined; pinned to 0
+            const float a = std::sqrt(rgba[4 * size_t(i) + c]) * 255.0f;
+            // (int)a is undefined for NaN and for values outside int's range: pinned to 0, the same explicit test as the
+            // device transform (pt_kernels.cuh f2c_sqrt), so the two produce identical bytes by construction
+            int b = 0;
+            if (a == a && a < 2147483648.0f && a >= -2147483648.0f) b = int(a);
             rgb[3 * size_t(i) + c] = uint8_t(b > 255 ? 255 : (b < 0 ? 0 : b));
         }
     return PTB_OK;

@@ -17,6 +17,7 @@
 #include <limits.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <cstddef>
@@ -93,6 +94,8 @@ class Device {
     }
     DeviceType m_type;
     ptb_device* m_dev;
+    ptb_device* m_helpers[PTB_MAX_PEERS] = {};  // other GPUs of the box that render part of this device's work (DeviceUtils::allocate)
+    int m_nHelpers = 0;
 
   private:
     enum { kMaxKernels = 8 };
@@ -105,9 +108,13 @@ class DeviceUtils {
   public:
     struct Config {
         enum DeviceType { DEVICE_GPU, DEVICE_CPU };
-        Config() : m_type(DEVICE_GPU), m_deviceIdx(0) {}
+        Config() : m_type(DEVICE_GPU), m_deviceIdx(0), m_nGpus(0) {}
         DeviceType m_type;
         int m_deviceIdx;
+        // not in the reference (it picks ONE device): how many GPUs of the box serve this device; 0 = the environment
+        // variable PTB_GPUS, else 1.  The flow does not change: the other GPUs become helpers (ptb_device_add_helper)
+        // and ptb_launch1d deals its frame-ahead batches over them, bit-identical to one GPU.
+        int m_nGpus;
     };
     static int getNDevices(DeviceType) {
         int n = 0;
@@ -118,11 +125,26 @@ class DeviceUtils {
     static Device* allocate(DeviceType, Config cfg = Config()) {
         ptb_device* d = nullptr;
         if (ptb_device_create(cfg.m_deviceIdx, &d) != PTB_OK) return nullptr;
-        return new Device(d);
+        Device* dev = new Device(d);
+        int want = cfg.m_nGpus;
+        if (want <= 0) {
+            const char* e = getenv("PTB_GPUS");
+            want = e ? atoi(e) : 1;
+        }
+        int have = 0;
+        ptb_device_count(&have);
+        for (int i = 1; i < want && i < have && dev->m_nHelpers < PTB_MAX_PEERS; ++i) {
+            ptb_device* h = nullptr;
+            if (ptb_device_create((cfg.m_deviceIdx + i) % have, &h) != PTB_OK) break;
+            if (ptb_device_add_helper(d, h) != PTB_OK) { ptb_device_destroy(h); break; }
+            dev->m_helpers[dev->m_nHelpers++] = h;
+        }
+        return dev;
     }
     static void deallocate(Device* device) {
         if (!device) return;
         ptb_device_destroy(device->m_dev);
+        for (int i = 0; i < device->m_nHelpers; ++i) ptb_device_destroy(device->m_helpers[i]);
         delete device;
     }
     static void waitForCompletion(const Device* device) {

@@ -3,7 +3,9 @@
 // the 64-byte Triangle/Material records by map/unmap, launch GenerateColors once per frame
 // with int4{W, H, frame, -}, wait, read the gamma-space framebuffer back, write the P3 PPM.
 //
-//   ptb_raycast [scene.bin] [out.ppm] [dimension=512] [frames=10000]
+//   ptb_raycast [scene.bin] [out.ppm] [dimension=512] [frames=10000] [gpus=1 | PTB_GPUS]
+// gpus > 1: the other GPUs of the box become helpers of device 0 (DeviceUtils::Config::m_nGpus -> ptb_device_add_helper);
+// the loop below does not change and the image is bit-identical to one GPU.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -28,6 +30,7 @@ int main(int argc, char** argv) {
         return 2;
     }
     DeviceUtils::Config cfg;
+    if (argc > 5) cfg.m_nGpus = std::atoi(argv[5]);
     Device* m_d = DeviceUtils::allocate(TYPE_CUDA, cfg);
     if (!m_d) {
         std::fprintf(stderr, "device allocation failed: %s\n", ptb_last_error());
@@ -103,7 +106,7 @@ int main(int argc, char** argv) {
                 std::fprintf(stderr, "writing %s failed: %s\n", path, ptb_last_error());
                 rc = 4;
             } else {
-                std::printf("%u frames of %dx%d -> %s\n", frames, dimension, dimension, path);
+                std::printf("%u frames of %dx%d on %d GPU(s) -> %s\n", frames, dimension, dimension, 1 + m_d->m_nHelpers, path);
             }
             DeviceUtils::waitForCompletion(m_d);
         }

@@ -493,9 +493,64 @@ def test_async_host_pipeline(dev, pt, cornell):
         dev.render_host_async(tris, mats, prm, pinned[0].array)
     with pytest.raises(pt.PtbError, match="in flight"):
         dev.render_host(tris, mats, prm)
-    dev.job_wait(j1); dev.job_wait(j2)
+    # waiting for the NEWER job first frees its slot for the next submit (any free slot is taken, not jobs_submitted & 1)
+    dev.job_wait(j2)
+    j3 = dev.render_host_async(tris, mats, prm, pageable[1])
+    dev.job_wait(j1); dev.job_wait(j3)
     for p in pinned:
         p.free()
+
+
+def test_async_reference_accumulation_is_sequential(dev, pt, ob, cornell):
+    """accum=REFERENCE continues the gamma-space running mean from the caller's out_rgba, read at submit time: a pipelined
+    submit while another job is in flight would use a stale state, so it is refused; the wait-then-submit loop equals the
+    synchronous path and the oracle, with pinned and with pageable buffers."""
+    tris, mats = cornell
+    w, h, n = 96, 64, 7
+    want, _, _ = ob.render(ob.default_params(w, h, first_frame=0, n_frames=n, mode=3, accum=ob.ACCUM_REFERENCE, max_depth=6), tris, mats)
+    pin = pt.PinnedArray((w * h, 4), np.float32)
+    for buf in (pin.array, np.zeros((w * h, 4), np.float32)):
+        buf[...] = 0
+        for f in range(n):
+            prm = pt.default_params(width=w, height=h, first_frame=f, n_frames=1, mode=pt.MODE_PATH, accum=pt.ACCUM_REFERENCE, max_depth=6)
+            dev.job_wait(dev.render_host_async(tris, mats, prm, buf))
+        np.testing.assert_array_equal(bits(buf), bits(want))
+    other = np.zeros((w * h, 4), np.float32)
+    j = dev.render_host_async(tris, mats, pt.default_params(width=w, height=h, first_frame=0, n_frames=1, mode=pt.MODE_PATH, max_depth=6), other)
+    with pytest.raises(pt.PtbError, match="wait for the job in flight"):
+        dev.render_host_async(tris, mats, pt.default_params(width=w, height=h, first_frame=1, n_frames=1, mode=pt.MODE_PATH, max_depth=6), pin.array)
+    dev.job_wait(j)
+    pin.free()
+
+
+def test_launch1d_sees_buffers_marked_dirty(dev, pt, cornell):
+    """A tBuffer rewritten behind its back (here: through a second view of its device pointer) keeps rendering the old scene until
+    ptb_buffer_mark_dirty tells ptb_launch1d to re-read it (the reference kernel re-reads its buffers on every launch)."""
+    tris, mats = cornell
+    w, h = 64, 48
+    tb, mb, fb = dev.buffer(36 * 64), dev.buffer(18 * 64), dev.buffer(w * h * 16)
+    tb.write(tris); mb.write(mats)
+    k = dev.kernel("GenerateColors", "GenerateColors")
+    dev.kernel_set_int(k, "BOUNCES", 16)
+    dev.launch1d(k, [tb, mb, fb], pt.Int4(w, h, 0, 0), w * h); dev.sync()
+    first = fb.read(np.uint32).copy()
+    t2 = tris.copy()
+    for key in ("p1", "p2", "p3"):
+        t2[key][16:36, 1] += 1.0  # lift both boxes
+    alias = dev.wrap(tb.device_ptr(), 36 * 64)
+    alias.write(t2)
+    alias.close()
+    dev.launch1d(k, [tb, mb, fb], pt.Int4(w, h, 0, 0), w * h); dev.sync()
+    assert np.array_equal(fb.read(np.uint32), first)  # documented: the resident scene is keyed on API writes
+    tb.mark_dirty()
+    dev.launch1d(k, [tb, mb, fb], pt.Int4(w, h, 0, 0), w * h); dev.sync()
+    lifted = fb.read(np.uint32).copy()
+    assert not np.array_equal(lifted, first)
+    tb2 = dev.buffer(36 * 64); tb2.write(t2)
+    dev.launch1d(k, [tb2, mb, fb], pt.Int4(w, h, 0, 0), w * h); dev.sync()
+    assert np.array_equal(fb.read(np.uint32), lifted)
+    for b in (tb, tb2, mb, fb):
+        b.close()
 
 
 def test_path_regeneration_equals_one_sample_per_thread(dev, pt, scene):
@@ -824,6 +879,105 @@ def test_launch1d_frame_ahead_batching(dev, pt, ob, cornell):
     dev.kernel_set_int(k, "FRAME_AHEAD", 1)
     dev.kernel_set_int(k, "BOUNCES", 16)
     tb.close(); mb.close()
+
+
+# ---- several GPUs in one process: ptb_device_add_helper / ptb_render_multi -------------------------------------------------
+
+def _helper_indices(pt, n):
+    """device indices for n helpers: the other GPUs of the box when there are any, else device 0 again (a second handle on the same
+    GPU takes every code path -- sharding, shared tree, cross-stream events -- only the stores are not remote)"""
+    import ctypes as C
+    c = C.c_int(0)
+    pt.lib().ptb_device_count(C.byref(c))
+    return [(1 + i) % max(1, c.value) for i in range(n)], c.value
+
+
+@pytest.mark.parametrize("n_helpers", [1, 3])
+def test_render_multi_is_bit_identical(pt, ob, cornell, n_helpers):
+    """ptb_render_multi: ONE image tile-sharded over a device and its helpers, host records in, host image out ==
+    ptb_render_host on one device == the oracle, for every mode, both accumulators and the 8-bit output."""
+    tris, mats = cornell
+    idx, n_gpus = _helper_indices(pt, n_helpers)
+    main = pt.Device(0)
+    single = pt.Device(0)
+    helpers = [pt.Device(i) for i in idx]
+    try:
+        for hlp in helpers:
+            main.add_helper(hlp)
+        assert main.helper_count() == n_helpers
+        with pytest.raises(pt.PtbError, match="serves one device"):
+            single.add_helper(helpers[0])
+        w, h = 200, 131
+        for mode in (0, 1, 2, 3):
+            prm = pt.default_params(width=w, height=h, n_frames=3, mode=mode, accum=pt.ACCUM_LINEAR, max_depth=6, frames_per_batch=2)
+            got, ctr = main.render_multi(tris, mats, prm)
+            want, _, wctr = single.render_host(tris, mats, prm)
+            np.testing.assert_array_equal(bits(got), bits(want), err_msg=f"mode {mode}")
+            assert ctr["rays_closest"] == wctr["rays_closest"] and ctr["rays_any"] == wctr["rays_any"] and ctr["samples"] == w * h * 3
+        # the reference's progressive state (gamma-space running mean) carried across calls, then the 8-bit output
+        fb = np.zeros((w * h, 4), np.float32)
+        for f0, nf in ((0, 2), (2, 3), (5, 1)):
+            prm = pt.default_params(width=w, height=h, first_frame=f0, n_frames=nf, mode=pt.MODE_PATH, accum=pt.ACCUM_REFERENCE, max_depth=5)
+            main.render_multi(tris, mats, prm, out=fb, want_counters=False)
+        ofb, _, _ = ob.render(ob.default_params(w, h, first_frame=0, n_frames=6, mode=3, accum=ob.ACCUM_REFERENCE, max_depth=5), tris, mats)
+        np.testing.assert_array_equal(bits(fb), bits(ofb))
+        prm = pt.default_params(width=w, height=h, n_frames=4, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR, max_depth=5, output=pt.OUTPUT_RGB8)
+        rgb, _ = main.render_multi(tris, mats, prm)
+        lin, _, _ = single.render_host(tris, mats, pt.default_params(width=w, height=h, n_frames=4, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR, max_depth=5))
+        np.testing.assert_array_equal(rgb, ob.to_rgb8(lin))
+        # a changed scene is picked up by every device; an image with fewer blocks than devices still renders
+        t2 = tris.copy()
+        t2["p1"][10:12, 1] -= 0.5
+        prm = pt.default_params(width=64, height=2, n_frames=2, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR, max_depth=4)
+        a, _ = main.render_multi(t2, mats, prm)
+        b, _, _ = single.render_host(t2, mats, prm)
+        np.testing.assert_array_equal(bits(a), bits(b))
+    finally:
+        helpers[0].close()   # a helper may go first ...
+        main.close()         # ... or after its device
+        for hlp in helpers[1:]:
+            hlp.close()
+        single.close()
+
+
+def test_launch1d_deals_frame_ahead_batches_over_helpers(pt, ob, cornell):
+    """The reference's progressive loop (RaytraceTest.cpp:250-268) through ptb_launch1d on a device WITH helpers: the frames of
+    each frame-ahead batch are traced by all devices into the main device's batch; the framebuffer after every launch equals
+    the single-device loop and, at the end, the oracle's."""
+    tris, mats = cornell
+    idx, n_gpus = _helper_indices(pt, 2)
+    main, single = pt.Device(0), pt.Device(0)
+    helpers = [pt.Device(i) for i in idx]
+    try:
+        for hlp in helpers:
+            main.add_helper(hlp)
+        w, h, nf = 128, 64, 45
+        states = {}
+        for name, d in (("multi", main), ("single", single)):
+            tb, mb, fb = d.buffer(36 * 64), d.buffer(18 * 64), d.buffer(w * h * 16)
+            tb.write(tris); mb.write(mats)
+            k = d.kernel("../test/ClKernels/GenerateColors", "GenerateColors")
+            out = []
+            for frame in range(nf):
+                if frame == 30:  # the scene changes in mid-sequence: every device must drop its copy
+                    t2 = tris.copy()
+                    t2["p1"][10:12, 1] -= 0.75
+                    tb.write(t2)
+                d.launch1d(k, [tb, mb, fb], pt.Int4(w, h, frame, 0), w * h)
+                d.sync()
+                out.append(fb.read(np.uint32).copy())
+            states[name] = out
+            for b in (tb, mb, fb):
+                b.close()
+        for i, (a, b) in enumerate(zip(states["multi"], states["single"])):
+            assert np.array_equal(a, b), f"frame {i}"
+        want, _, _ = ob.render(ob.default_params(w, h, first_frame=0, n_frames=30, mode=3, accum=ob.ACCUM_REFERENCE), tris, mats)
+        assert np.array_equal(states["multi"][29], bits(want).reshape(-1))
+    finally:
+        main.close()
+        for hlp in helpers:
+            hlp.close()
+        single.close()
 
 
 @pytest.mark.parametrize("integrator", ["mega", "wavefront"])
