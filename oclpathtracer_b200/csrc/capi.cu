@@ -664,18 +664,41 @@ static int set_smem(K kernel, size_t smem, int block, int* per_sm = nullptr) {
 template <int MODE, bool BVH, int SMALL, bool STATS>
 static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::RenderArgs& a) {
     const int block = (a.tune[3] == 64 || a.tune[3] == 32) ? a.tune[3] : 128;
-    if (MODE == PTB_MODE_PATH && a.tune[5] == 0) {  // persistent grid with path regeneration (tune[5]=1: one sample per thread)
+    if (MODE == PTB_MODE_PATH && a.tune[5] != 1) {  // persistent grid with path regeneration (tune[5]=1: one sample per thread)
         // tune[9] = extra KB of (unused) shared memory per CTA: lowers the occupancy for latency-sensitivity measurements
         const size_t smem = ptd::scene_smem_bytes(sc, BVH, SMALL, block) + (a.tune[9] > 0 ? size_t(a.tune[9]) * 1024 : 0);
-        auto k = ptd::k_mega_path_regen<BVH, SMALL, STATS>;
-        int per_sm = 0;
-        if (int rc = set_smem(k, smem, block, &per_sm)) return rc;
+        // Two schedules of the same per-sample arithmetic: k_path_sm (per-lane state machine, the warp votes the phase) and
+        // k_mega_path_regen (while-while query inside a path segment).  tune[5] = 2 / 3 forces the latter / the former.
+        bool state_machine = BVH && SMALL == ptd::PTD_LARGE;
+        if (a.tune[5] == 2) state_machine = false;
+        if (a.tune[5] == 3) state_machine = BVH;
         const long long total = (long long)a.frames_in_batch * a.n_local;
-        long long grid = (long long)per_sm * dev->prop.multiProcessorCount;
         const long long need = (total + block - 1) / block;
-        if (grid > need) grid = need;
         unsigned long long* work = dev->counters + 32;
         CU_TRY(cudaMemsetAsync(work, 0, sizeof(unsigned long long), dev->stream));
+        int per_sm = 0;
+        if constexpr (BVH) {
+            if (state_machine) {
+                // Large scenes: every node comes from global memory (the top of the tree stays in L1 anyway; tune[4] = n stages
+                // an n-node prefix as k_mega_path_regen does), which lets the node visit run without divergent paths.
+                ptd::SceneDev sc2 = sc;
+                if (SMALL == ptd::PTD_LARGE && a.tune[4] == 0) sc2.smem_nodes = 0;
+                const size_t smem2 = ptd::scene_smem_bytes(sc2, BVH, SMALL, block) + (a.tune[9] > 0 ? size_t(a.tune[9]) * 1024 : 0);
+                // tune[12] = 1: let ptxas use the registers it wants (7 CTAs per SM on the large-scene form) instead of capping at 64 (8 CTAs)
+                auto k = ptd::k_path_sm<SMALL, STATS, 0>;
+                if constexpr (SMALL == ptd::PTD_LARGE && !STATS) if (a.tune[12] != 1) k = ptd::k_path_sm<SMALL, STATS, 8>;
+                if (int rc = set_smem(k, smem2, block, &per_sm)) return rc;
+                long long grid = (long long)per_sm * dev->prop.multiProcessorCount;
+                if (grid > need) grid = need;
+                k<<<(unsigned)grid, block, smem2, dev->stream>>>(sc2, a, work);
+                CU_TRY(cudaGetLastError());
+                return PTB_OK;
+            }
+        }
+        auto k = ptd::k_mega_path_regen<BVH, SMALL, STATS>;
+        if (int rc = set_smem(k, smem, block, &per_sm)) return rc;
+        long long grid = (long long)per_sm * dev->prop.multiProcessorCount;
+        if (grid > need) grid = need;
         k<<<(unsigned)grid, block, smem, dev->stream>>>(sc, a, work);
         CU_TRY(cudaGetLastError());
         return PTB_OK;

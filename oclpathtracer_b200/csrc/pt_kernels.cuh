@@ -158,20 +158,17 @@ struct RayCount {
     uint32_t closest, any;
 };
 
-// One iteration of the path loop, GenerateColors.cl:229-258.  Returns true when the path goes on
-// (r, mask, seed updated), false when it ended; radiance accumulates either way.
-template <bool BVH, int SMALL, bool STATS>
-PTD_FI bool path_segment(const Ctx& c, Ray& r, uint32_t& seed, V3& radiance, V3& mask, int i, int max_depth,
-                         SampleStats<STATS>& st, RayCount& rc, QueryStats& qs) {
-    Hit h;
-    const uint32_t v0 = qs.visits;
-    const bool hit = q_closest<BVH, SMALL, STATS>(c, r.o, r.d, h, qs);
-    rc.closest++;
+// The part of one path-loop iteration that follows the scene query, GenerateColors.cl:233-257: `hit`/`h` are the query's
+// result, `visits` its node visits.  Returns true when the path goes on (r, mask, seed updated), false when it ended;
+// radiance accumulates either way.
+template <int SMALL, bool STATS>
+PTD_FI bool path_after_hit(const Ctx& c, bool hit, const Hit& h, Ray& r, uint32_t& seed, V3& radiance, V3& mask, int i,
+                           int max_depth, SampleStats<STATS>& st, uint32_t visits) {
     V3 p1, e1, e2; int idx = -1, quad = -1;
     if (hit) load_tri<SMALL>(c, h.pos, p1, e1, e2, idx, quad);
     if constexpr (STATS) {
-        if (i == 0) st_primary(st, hit, h, quad, qs.visits - v0);
-        else st_secondary(st, hit ? h.idx : -1, qs.visits - v0);
+        if (i == 0) st_primary(st, hit, h, quad, visits);
+        else st_secondary(st, hit ? h.idx : -1, visits);
         st.count++;
     }
     if (!hit) {  // :233-237, max(bg, 0) = bg
@@ -195,6 +192,17 @@ PTD_FI bool path_segment(const Ctx& c, Ray& r, uint32_t& seed, V3& radiance, V3&
     mask = mk(mask.x * (color.x * dw / pdf), mask.y * (color.y * dw / pdf), mask.z * (color.z * dw / pdf));  // :253-255
     r = get_ray(add(p, mul(wi, 0.01f)), wi);                      // :257
     return true;
+}
+
+// One iteration of the path loop, GenerateColors.cl:229-258: the scene query, then path_after_hit.
+template <bool BVH, int SMALL, bool STATS>
+PTD_FI bool path_segment(const Ctx& c, Ray& r, uint32_t& seed, V3& radiance, V3& mask, int i, int max_depth,
+                         SampleStats<STATS>& st, RayCount& rc, QueryStats& qs) {
+    Hit h;
+    const uint32_t v0 = qs.visits;
+    const bool hit = q_closest<BVH, SMALL, STATS>(c, r.o, r.d, h, qs);
+    rc.closest++;
+    return path_after_hit<SMALL, STATS>(c, hit, h, r, seed, radiance, mask, i, max_depth, st, qs.visits - v0);
 }
 
 // GenerateColors.cl:223-261 with BOUNCES -> max_depth
@@ -430,6 +438,203 @@ __global__ void __launch_bounds__(128) k_mega_path_regen(const SceneDev sc, cons
                 }
                 alive = false;
             }
+        }
+    }
+    flush_counter(a.counters, CTR_CLOSEST, rc.closest);
+    if (STATS) {
+        flush_counter(a.counters, CTR_NODES, qs.visits);
+        flush_counter(a.counters, CTR_TESTS, qs.tests);
+    }
+}
+
+// ---- path kernel as a per-lane state machine ("phase voting") ---------------------------------------------------------
+// k_mega_path_regen keeps the classic while-while query inside one path segment: a warp leaves the node loop only when its
+// slowest lane reached a leaf and leaves the segment only when its slowest query ended.  On a deep tree with incoherent rays
+// the per-ray node count is heavy-tailed (2M-triangle scene: 23.7 on average, several times that for rays grazing a
+// tessellated wall), so the node loop ran at 11 of 32 lanes (profiles/r02/ncu_k_mega_path_regen_c5_before_blocks.txt).
+// Here every lane carries an explicit state and the WARP votes which phase runs next:
+//     NODE   ONE node visit (tree forms) / the leaf-box sweep (FLAT)        } the inner "walk" loop: runs until thr_shade
+//     LEAF   ONE triangle test, then the next triangle of the leaf or a pop  } lanes finished their query (or nobody walks)
+//     SHADE  the part of the path loop after the query (path_after_hit)
+//     REGEN  draw the next sample slot, generate the camera ray   (>= thr_regen lanes wait, or nothing else is left to do)
+// so a phase runs for all lanes that need it, lanes of other states wait at most until their own phase collects its quorum,
+// and a ray that walks 200 nodes no longer holds 31 finished lanes.  Per ray the order of node visits, triangle tests,
+// culling and RNG draws is exactly bvh_query's / path_segment's -> results, visit and test counts are bit-identical.
+// States are one-hot BYTES of one word, so that ONE warp reduction (REDUX.SUM) counts the lanes of all states at once.
+enum : uint32_t { ST_DONE = 0u, ST_REGEN = 1u, ST_NODE = 1u << 8, ST_LEAF = 1u << 16, ST_SHADE = 1u << 24 };
+
+// Visit of a BINARY node from global memory with the stack in local memory (the 2M-triangle scene's form).  Same rule as
+// node_step2 (DESIGN.md "Traversal order") with the common outcomes free of divergent paths: every lane fetches its node
+// and, speculatively, its stack top together; descend / push / pop-of-a-live-entry are selects and one predicated store.
+// Only a pop that meets culled entries (entry distance > best_t) loops.  False = the query finished.
+template <bool STATS>
+PTD_FI bool node_step2_bf(const Ctx& c, V3 invd, V3 ood, float best_t, int& cur, int& sp, QueryStats& qs) {
+    const float4* p = c.g_nodes + 4 * (size_t)cur;
+    float4 n0, n1, n2, n3;
+    ldg256(p, n0, n1); ldg256(p + 2, n2, n3);
+    const uint2 top = c.lstack[sp > 0 ? sp - 1 : 0];
+    if (STATS) qs.visits++;
+    float tn0, tn1;
+    const V3 ainv = mk(fabsf(invd.x), fabsf(invd.y), fabsf(invd.z));
+    const bool h0 = slab(xyz(n0), xyz(n1), invd, ainv, ood, best_t, tn0);
+    const bool h1 = slab(xyz(n2), xyz(n3), invd, ainv, ood, best_t, tn1);
+    const int c0 = __float_as_int(n0.w), c1 = __float_as_int(n1.w);
+    const bool second_first = tn1 < tn0;
+    const bool both = h0 && h1;
+    if (both) c.lstack[sp] = make_uint2((uint32_t)(second_first ? c0 : c1), __float_as_uint(second_first ? tn0 : tn1));
+    if (h0 || h1) {
+        cur = both ? (second_first ? c1 : c0) : (h0 ? c0 : c1);
+        sp += both ? 1 : 0;
+        return true;
+    }
+    if (sp == 0) return false;
+    --sp;
+    cur = (int)top.x;
+    if (__uint_as_float(top.y) <= best_t) return true;
+    while (sp > 0) {  // culled entries
+        --sp;
+        const uint2 e = c.lstack[sp];
+        cur = (int)e.x;
+        if (__uint_as_float(e.y) <= best_t) return true;
+    }
+    return false;
+}
+
+template <int SMALL, bool STATS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_path_sm(const SceneDev sc, const RenderArgs a, unsigned long long* work_counter) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Ctx c = stage_scene<true, SMALL>(sc, smem);
+    uint2 lstack_mem[PTD_LSTACK_ENTRIES];
+    if (!SMALL && sc.lstack) c.lstack = lstack_mem;
+    const bool fast_nodes = SMALL == PTD_LARGE && sc.lstack && sc.smem_nodes == 0;  // warp-uniform: node_step2_bf applies
+    const long long total = (long long)a.frames_in_batch * a.n_local;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t thr_regen = a.tune[0] > 0 ? a.tune[0] : 6;
+    const uint32_t thr_shade = a.tune[10] > 0 ? a.tune[10] : 12;
+    const uint32_t thr_leaf = a.tune[11] > 0 ? a.tune[11] : 10;
+    RayCount rc{0u, 0u};
+    QueryStats qs{0u, 0u};
+    uint32_t state = ST_REGEN;
+    bool exhausted = false;  // warp-uniform: the work counter ran past the last sample slot
+    long long slot = 0;
+    int li = 0, frame = 0, depth = 0;
+    uint32_t seed = 0, tests0 = 0, visits0 = 0;
+    Ray r{mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 1.f)};
+    V3 radiance = mk(0.f, 0.f, 0.f), mask = mk(1.f, 1.f, 1.f);
+    // query state
+    V3 invd = mk(0.f, 0.f, 0.f), ood = invd;
+    float best_t = 1e20f, best_u = 0.f, best_v = 0.f;
+    int best_pos = -1, best_idx = -1, cur = 0, sp = 0;
+    unsigned long long tm = 0ull;  // FLAT: triangles still to test
+    SampleStats<STATS> st{};
+    auto begin_query = [&]() {  // the ray in `r` starts its closest-hit query (bvh_query's / flat_query's preamble)
+        visits0 = qs.visits;
+        best_t = 1e20f; best_u = best_v = 0.f; best_pos = best_idx = -1;
+        if constexpr (SMALL != PTD_FLAT) {
+            invd = safe_rcp3(r.d);
+            ood = mk(r.o.x * invd.x, r.o.y * invd.y, r.o.z * invd.z);
+            cur = 0; sp = 0;
+        }
+        state = ST_NODE;
+    };
+    for (;;) {
+        // ---- walk: node visits and triangle tests until thr_shade lanes have finished their query, or nobody walks
+        for (;;) {
+            const uint32_t cnt = __reduce_add_sync(0xffffffffu, state);
+            const uint32_t n_node = (cnt >> 8) & 255u, n_leaf = (cnt >> 16) & 255u, n_shade = cnt >> 24;
+            if (n_leaf >= thr_leaf || (n_leaf && !n_node)) {
+                if (state == ST_LEAF) {
+                    int k;
+                    if constexpr (SMALL == PTD_FLAT) {
+                        k = __ffsll((long long)tm) - 1;
+                        tm &= tm - 1ull;
+                    } else {
+                        k = (int)((uint32_t)(~cur) >> 3);
+                    }
+                    V3 p1, e1, e2; int idx, quad;
+                    load_tri<SMALL>(c, k, p1, e1, e2, idx, quad);
+                    float t, u, v;
+                    if (STATS) qs.tests++;
+                    if (mt_core(r.o, r.d, p1, e1, e2, t, u, v) && (t < best_t || (t == best_t && best_idx >= 0 && idx < best_idx))) {
+                        best_t = t; best_u = u; best_v = v; best_pos = k; best_idx = idx;
+                    }
+                    if constexpr (SMALL == PTD_FLAT) {
+                        if (!tm) state = ST_SHADE;
+                    } else {
+                        const uint32_t code = (uint32_t)(~cur);
+                        if (code & 7u) cur = (int)~(((code >> 3) + 1u) << 3 | ((code & 7u) - 1u));  // the next triangle of this leaf
+                        else if (stack_pop<false>(c, sp, cur, best_t)) state = cur >= 0 ? ST_NODE : ST_LEAF;
+                        else state = ST_SHADE;
+                    }
+                }
+                continue;
+            }
+            if (!n_node || n_shade >= thr_shade) break;
+            if (state == ST_NODE) {
+                if constexpr (SMALL == PTD_FLAT) {
+                    tm = flat_boxes<STATS>(c, r.o, r.d, 1e20f, qs);
+                    state = tm ? ST_LEAF : ST_SHADE;
+                } else {
+                    bool more;
+                    if (SMALL == PTD_LARGE && fast_nodes) more = node_step2_bf<STATS>(c, invd, ood, best_t, cur, sp, qs);
+                    else more = node_step<false, SMALL, STATS>(c, invd, ood, best_t, cur, sp, qs);
+                    state = !more ? ST_SHADE : cur >= 0 ? ST_NODE : ST_LEAF;
+                }
+            }
+        }
+        // ---- shade every lane whose query finished
+        if (state == ST_SHADE) {
+            Hit h;
+            const bool hit = best_idx >= 0;
+            h.t = best_t; h.u = best_u; h.v = best_v; h.pos = best_pos; h.idx = best_idx;
+            rc.closest++;
+            const bool more = path_after_hit<SMALL, STATS>(c, hit, h, r, seed, radiance, mask, depth, a.max_depth, st, qs.visits - visits0);
+            ++depth;
+            if (!more || depth >= a.max_depth) {
+                a.samples[slot] = make_float4(cl_max(radiance.x, 0.0f), cl_max(radiance.y, 0.0f), cl_max(radiance.z, 0.0f), 1.0f);  // :260
+                if constexpr (STATS) {
+                    if (a.stats && frame == a.stats_frame) {
+                        uint4* dst = reinterpret_cast<uint4*>(a.stats + li);
+                        dst[0] = make_uint4((uint32_t)st.tri, (uint32_t)st.quad, st.t_bits, st.visits_primary);
+                        dst[1] = make_uint4(st.visits_secondary, st.count, st.id_hash, qs.tests - tests0);
+                    }
+                }
+                state = exhausted ? ST_DONE : ST_REGEN;
+            } else {
+                begin_query();
+            }
+        }
+        // ---- new samples for the lanes whose path ended: when thr_regen of them wait, or when nothing else is left to do
+        const unsigned m_regen = __ballot_sync(0xffffffffu, state == ST_REGEN);
+        const unsigned m_walk = __ballot_sync(0xffffffffu, (state & (ST_NODE | ST_LEAF)) != 0u);
+        const uint32_t n_regen = __popc(m_regen);
+        if (n_regen && (n_regen >= thr_regen || !m_walk)) {  // (lanes are never in REGEN once `exhausted` is set)
+            const int leader = __ffs(m_regen) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)n_regen);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if ((long long)base + (long long)n_regen >= total) exhausted = true;
+            if (state == ST_REGEN) {
+                slot = (long long)base + __popc(m_regen & ((1u << lane) - 1u));
+                if (slot >= total) {
+                    state = ST_DONE;
+                } else {
+                    const int fi = (int)(slot / a.n_local);
+                    li = (int)(slot - (long long)fi * a.n_local);
+                    const int gid = gid_of_local(a.shard, li);
+                    frame = a.first_frame + fi;
+                    seed = (uint32_t)gid + hash_uint32((uint32_t)frame);                    // GenerateColors.cl:308
+                    r = generate_ray(gid % a.width, gid / a.width, CamScale{a.cam_inv_w, a.cam_inv_h, a.cam_aspect}, seed);  // :310
+                    radiance = mk(0.f, 0.f, 0.f);
+                    mask = mk(1.f, 1.f, 1.f);
+                    depth = 0;
+                    st = SampleStats<STATS>{};
+                    tests0 = qs.tests;
+                    begin_query();
+                }
+            }
+        } else if (!m_walk) {
+            break;  // nobody walks, nobody waits for a sample, every query was shaded: all lanes are DONE
         }
     }
     flush_counter(a.counters, CTR_CLOSEST, rc.closest);

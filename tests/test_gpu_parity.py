@@ -570,6 +570,43 @@ def test_path_regeneration_equals_one_sample_per_thread(dev, pt, scene):
     assert res[0] == res[1]
 
 
+@pytest.mark.parametrize("form", ["flat", "wide4", "binary_smem", "binary_global"])
+def test_path_state_machine_is_scheduling_only(dev, pt, cornell, form):
+    """k_path_sm (per-lane state machine, the warp votes which phase runs: tune[5]=3) against k_mega_path_regen (tune[5]=2)
+    and the one-sample-per-thread megakernel (tune[5]=1), for every scene form and for quorum thresholds from 1 to 32
+    (tune[0] regen, tune[10] shade, tune[11] leaf): radiance bits, per-pixel statistics and counters must not move."""
+    tris, mats = cornell
+    if form == "binary_global":
+        sc = dev.scene(pt.tessellate(tris, 12), mats)
+        assert sc.info()["width"] == 2 and sc.info()["n_nodes"] > 64
+    else:
+        sc = dev.scene(tris, mats, pt.bvh_params(force_width={"flat": 1, "wide4": 4, "binary_smem": 2}[form]))
+    w, h = 333, 77
+    kw = dict(width=w, height=h, n_frames=3, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR, max_depth=9, collect_stats=1,
+              integrator=pt.INTEGRATOR_MEGAKERNEL, frames_per_batch=2)
+    res = []
+    try:
+        for variant, thr in ((1, (0, 0, 0)), (2, (0, 0, 0)), (3, (0, 0, 0)), (3, (1, 1, 1)), (3, (32, 32, 32)), (3, (3, 20, 2)), (3, (12, 2, 27))):
+            dev.set_tuning(5, variant)
+            for k, v in zip((0, 10, 11), thr):
+                dev.set_tuning(k, v)
+            for stats_on in (1, 0):
+                frame, stats = dev.buffer(w * h * 16), dev.buffer(w * h * 32)
+                ctr = dev.render(sc, pt.default_params(**{**kw, "collect_stats": stats_on}), frame, stats if stats_on else None, want_counters=True)
+                res.append((variant, thr, stats_on, frame.read(np.uint32).tobytes(), stats.read(np.uint32).tobytes() if stats_on else b"",
+                            (ctr["rays_closest"], ctr["samples"]) + ((ctr["nodes"], ctr["tri_tests"]) if stats_on else ())))
+                frame.close(); stats.close()
+    finally:
+        for k in (5, 0, 10, 11):
+            dev.set_tuning(k, 0)
+        sc.close()
+    for r in res:
+        ref = res[0] if r[2] else res[1]
+        assert r[3] == ref[3], (form, r[:3], "radiance")
+        assert r[4] == ref[4], (form, r[:3], "stats")
+        assert r[5] == ref[5], (form, r[:3], "counters")
+
+
 @pytest.mark.parametrize("mode", [1, 2, 3])
 def test_wavefront_persistent_fetch_is_scheduling_only(dev, pt, scene, mode):
     """tune[6]/tune[7]: persistent traversal with dynamic ray fetch (any refill threshold) vs one thread per ray."""
