@@ -20,6 +20,7 @@
 // remaining subtrees follow depth-first.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 

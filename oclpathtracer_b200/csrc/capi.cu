@@ -623,9 +623,11 @@ static ptd::SceneDev scene_dev(const ptb_scene* s, int cls) {
         d.stack_depth = 3 * s->built().depth4 + 1;
         return d;
     }
-    // Large scenes stage only the top of the tree: a 64-node (4 KB) prefix keeps >= 6 CTAs per SM
-    // resident (measured on the 2M-triangle scene: 1024 nodes 0.83, 256 nodes 1.81, 64 nodes 2.28 Grays/s).
-    const int cap = s->dev->tune[4] > 0 ? s->dev->tune[4] : 64;
+    // Large scenes stage nothing by default: the top of the tree stays in L1 anyway, shared memory left unused is L1 capacity
+    // (which the local-memory traversal stacks need), and a node visit without the "staged or global?" fork runs free of
+    // divergent paths (node_step2_bf).  tune[4] = n stages an n-node prefix (round 1 measured 1024 nodes 0.83, 256 nodes 1.81,
+    // 64 nodes 2.28 Grays/s on the 2M-triangle scene; round 2: 64 -> 0 nodes +1 %).
+    const int cap = s->dev->tune[4] > 0 ? s->dev->tune[4] : 0;
     d.smem_nodes = s->small ? s->bfs_nodes : (s->bfs_nodes < cap ? s->bfs_nodes : cap);
     d.small = s->small ? 1 : 0;
     d.flat_n = 0;
@@ -686,7 +688,10 @@ static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::Re
                 const size_t smem2 = ptd::scene_smem_bytes(sc2, BVH, SMALL, block) + (a.tune[9] > 0 ? size_t(a.tune[9]) * 1024 : 0);
                 // tune[12] = 1: let ptxas use the registers it wants (7 CTAs per SM on the large-scene form) instead of capping at 64 (8 CTAs)
                 auto k = ptd::k_path_sm<SMALL, STATS, 0>;
-                if constexpr (SMALL == ptd::PTD_LARGE && !STATS) if (a.tune[12] != 1) k = ptd::k_path_sm<SMALL, STATS, 8>;
+                if constexpr (SMALL == ptd::PTD_LARGE && !STATS) {
+                    if (a.tune[12] != 1) k = ptd::k_path_sm<SMALL, STATS, 8>;
+                    if (a.tune[12] == 9) k = ptd::k_path_sm<SMALL, STATS, 9>;
+                }
                 if (int rc = set_smem(k, smem2, block, &per_sm)) return rc;
                 long long grid = (long long)per_sm * dev->prop.multiProcessorCount;
                 if (grid > need) grid = need;
@@ -807,7 +812,14 @@ static int render_impl(ptb_device* dev, ptb_scene* scene, const ptb_render_param
     // batch of frames kept in flight
     int fpb = p->frames_per_batch;
     if (fpb <= 0) {
-        const long long target = 4ll << 20;
+        // Sample slots in flight per launch.  A persistent path kernel ends with a tail in which the few longest walks run
+        // alone (a ray grazing a tessellated wall visits hundreds of nodes): with one 4K frame per launch that tail was
+        // 11 % of the 2M-triangle scene's time (16 frames per launch: 3.35 -> 3.76 Grays/s; Cornell box at 4K +2.6 %).
+        // 128 Mi slots = 2 GB of samples; the wavefront integrator, which keeps ~150 bytes of queues per slot, stays at 32 Mi.
+        // tune[15] = log2 of the slot target overrides (A/B runs).
+        const bool wavefront = p->integrator == PTB_INTEGRATOR_WAVEFRONT;
+        long long target = p->mode == PTB_MODE_PATH ? (wavefront ? 32ll << 20 : 128ll << 20) : 4ll << 20;
+        if (dev->tune[15] > 0 && dev->tune[15] < 31) target = 1ll << dev->tune[15];
         fpb = (int)((target + n_local - 1) / n_local);
     }
     if (fpb > p->n_frames) fpb = p->n_frames;

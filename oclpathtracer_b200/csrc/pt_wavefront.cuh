@@ -193,6 +193,91 @@ PTD_FI void trace_persistent(const Ctx& c, IO& io, const unsigned int n_rays, un
     }
 }
 
+// The same persistent traversal as a per-lane state machine (see k_path_sm): the warp votes whether the next step is a
+// refill (>= refill_thr lanes idle), ONE triangle test for the lanes at a leaf (>= thr_leaf of them, or nobody at a node) or
+// ONE node visit for the others, so a lane on a long walk never waits for the leaves of its neighbours and a fresh ray's
+// long first descent does not stall lanes that are between two leaves.  Per ray the sequence of node visits, triangle tests
+// and culls is bvh_query's: results and counts are identical.  Used for scenes traversed from L2/HBM.
+template <bool ANY, int SMALL, bool STATS, class IO>
+PTD_FI void trace_persistent_sm(const Ctx& c, IO& io, const unsigned int n_rays, unsigned int* work_counter,
+                                const uint32_t refill_thr, const uint32_t thr_leaf, const bool fast_nodes, uint32_t& n_traced,
+                                QueryStats& total) {
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t state = ST_REGEN;  // ST_REGEN = idle: the lane wants a ray
+    bool exhausted = false;     // warp-uniform
+    unsigned int idx = 0;
+    V3 o = mk(0.f, 0.f, 0.f), d = o, invd = o, ood = o;
+    float best_t = 0.f, best_u = 0.f, best_v = 0.f;
+    int best_pos = -1, best_idx = -1, cur = 0, sp = 0;
+    bool blocked = false;
+    QueryStats qs{0u, 0u};
+    auto finish = [&]() {
+        Hit h;
+        const bool hit = ANY ? blocked : best_idx >= 0;
+        h.t = best_t; h.u = best_u; h.v = best_v; h.pos = best_pos; h.idx = hit ? best_idx : -1;
+        io.store(idx, hit, h, qs);
+        if (STATS) { total.visits += qs.visits; total.tests += qs.tests; }
+        state = ST_REGEN;
+    };
+    for (;;) {
+        const uint32_t cnt = __reduce_add_sync(0xffffffffu, state);
+        const uint32_t n_idle = cnt & 255u, n_node = (cnt >> 8) & 255u, n_leaf = (cnt >> 16) & 255u;
+        const bool walking = (n_node | n_leaf) != 0u;
+        if (!exhausted && n_idle && (n_idle >= refill_thr || !walking)) {
+            const unsigned idle = __ballot_sync(0xffffffffu, state == ST_REGEN);
+            const int leader = __ffs(idle) - 1;
+            unsigned int base = 0;
+            if ((int)lane == leader) base = atomicAdd(work_counter, n_idle);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (state == ST_REGEN) {
+                idx = base + (unsigned int)__popc(idle & ((1u << lane) - 1u));
+                float tmax;
+                if (idx < n_rays && io.load(idx, o, d, tmax)) {
+                    invd = safe_rcp3(d);
+                    ood = mk(o.x * invd.x, o.y * invd.y, o.z * invd.z);
+                    best_t = tmax; best_u = best_v = 0.f; best_pos = best_idx = -1;
+                    cur = 0; sp = 0; blocked = false;
+                    qs.visits = qs.tests = 0u;
+                    state = ST_NODE;
+                    ++n_traced;
+                }
+            }
+            if (base + n_idle >= n_rays) exhausted = true;
+            continue;
+        }
+        if (n_leaf >= thr_leaf || (n_leaf && !n_node)) {
+            if (state == ST_LEAF) {
+                const uint32_t code = (uint32_t)(~cur);
+                const int k = (int)(code >> 3);
+                V3 p1, e1, e2; int tidx, quad;
+                load_tri<SMALL>(c, k, p1, e1, e2, tidx, quad);
+                float t, u, v;
+                if (STATS) qs.tests++;
+                if (mt_core(o, d, p1, e1, e2, t, u, v)) {
+                    if (ANY) {
+                        if (t < best_t) { best_t = t; best_u = u; best_v = v; best_pos = k; best_idx = tidx; blocked = true; }
+                    } else if (t < best_t || (t == best_t && best_idx >= 0 && tidx < best_idx)) {
+                        best_t = t; best_u = u; best_v = v; best_pos = k; best_idx = tidx;
+                    }
+                }
+                if (ANY && blocked) finish();
+                else if (code & 7u) cur = (int)~(((code >> 3) + 1u) << 3 | ((code & 7u) - 1u));  // the next triangle of this leaf
+                else if (stack_pop<ANY>(c, sp, cur, best_t)) state = cur >= 0 ? ST_NODE : ST_LEAF;
+                else finish();
+            }
+            continue;
+        }
+        if (!n_node) break;  // nobody walks and the idle lanes cannot be refilled
+        if (state == ST_NODE) {
+            bool more;
+            if (!ANY && SMALL == PTD_LARGE && fast_nodes) more = node_step2_bf<STATS>(c, invd, ood, best_t, cur, sp, qs);
+            else more = node_step<ANY, SMALL, STATS>(c, invd, ood, best_t, cur, sp, qs);
+            if (!more) finish();
+            else state = cur >= 0 ? ST_NODE : ST_LEAF;
+        }
+    }
+}
+
 struct ExtendIO {
     const float4* qo;
     const float4* qd;
@@ -237,7 +322,7 @@ struct ExtendStore : ExtendIO {
 
 template <int SMALL, bool STATS>
 __global__ void __launch_bounds__(128) wf_extend_p(const SceneDev sc, const WfBuffers w, const int depth, const int qi,
-                                                   unsigned long long* counters, const int refill_thr) {
+                                                   unsigned long long* counters, const int refill_thr, const int sm_thr_leaf) {
     const unsigned int n = w.counts[depth];
     if (blockIdx.x * blockDim.x >= n) return;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -249,7 +334,12 @@ __global__ void __launch_bounds__(128) wf_extend_p(const SceneDev sc, const WfBu
     io.c = &c;
     uint32_t nrays = 0;
     QueryStats total{0u, 0u};
-    trace_persistent<false, SMALL, STATS>(c, io, n, w.work + depth, refill_thr, nrays, total);
+    // tune[13] = 1: the while-while form for every scene class; default: the state-machine form for scenes traversed from L2/HBM
+    if (SMALL == PTD_LARGE && sm_thr_leaf > 0)
+        trace_persistent_sm<false, SMALL, STATS>(c, io, n, w.work + depth, (uint32_t)refill_thr, (uint32_t)sm_thr_leaf,
+                                                 sc.lstack && sc.smem_nodes == 0, nrays, total);
+    else
+        trace_persistent<false, SMALL, STATS>(c, io, n, w.work + depth, refill_thr, nrays, total);
     flush_counter(counters, CTR_CLOSEST, nrays);
     if (STATS) {
         flush_counter(counters, CTR_NODES, total.visits);
@@ -632,6 +722,7 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
     // tune[6]=1: one thread per ray (no dynamic fetch).  FLAT scenes have no node loop to keep busy: one thread per ray.
     const bool persist = BVH && SMALL != PTD_FLAT && a.tune[6] == 0;
     const int refill_thr = a.tune[7] > 0 ? a.tune[7] : 8;  // idle lanes that trigger a refill
+    const int sm_thr_leaf = a.tune[13] == 1 ? 0 : (a.tune[11] > 0 ? a.tune[11] : 10);  // state-machine extend: lanes at a leaf that trigger a triangle step
     auto pgrid = [&](auto kernel, size_t smem, long long n_items) -> unsigned {
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -655,7 +746,7 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
         const unsigned pg = persist ? pgrid(extp, smem_q, P) : 0u;
         for (int depth = 0; depth < a.max_depth; ++depth) {
             const int qi = depth & 1;
-            if (persist) extp<<<pg, block, smem_q, st>>>(sc, w, depth, qi, counters, refill_thr);
+            if (persist) extp<<<pg, block, smem_q, st>>>(sc, w, depth, qi, counters, refill_thr, sm_thr_leaf);
             else ext<<<grid, block, smem_q, st>>>(sc, w, depth, qi, counters);
             shade<<<grid, block, smem_s, st>>>(sc, a, w, depth, qi);
             *launches += 2;
@@ -665,7 +756,7 @@ static int wf_run(cudaStream_t st, int mode, const SceneDev& sc, const RenderArg
         if (persist) {
             auto extp = wf_extend_p<SMALL == PTD_FLAT ? PTD_SMALL4 : SMALL, STATS>;
             if ((rc = wf_smem(extp, smem_q))) return rc;
-            extp<<<pgrid(extp, smem_q, P), block, smem_q, st>>>(sc, w, 0, 0, counters, refill_thr);
+            extp<<<pgrid(extp, smem_q, P), block, smem_q, st>>>(sc, w, 0, 0, counters, refill_thr, sm_thr_leaf);
         } else {
             ext<<<grid, block, smem_q, st>>>(sc, w, 0, 0, counters);
         }

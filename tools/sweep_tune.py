@@ -28,9 +28,15 @@ def main():
         tris = pt.tessellate(tris, wl["tess"])
     dev = pt.Device(0)
     bp = None
-    if os.environ.get("SWEEP_FORCE_WIDTH"):
-        bp = pt.bvh_params(force_width=int(os.environ["SWEEP_FORCE_WIDTH"]))
+    if os.environ.get("SWEEP_FORCE_WIDTH") or os.environ.get("SWEEP_MAX_LEAF") or os.environ.get("SWEEP_SAH_TRAVERSE"):
+        bp = pt.bvh_params()
+        bp.force_width = int(os.environ.get("SWEEP_FORCE_WIDTH", "0"))
+        if os.environ.get("SWEEP_MAX_LEAF"):
+            bp.max_leaf = int(os.environ["SWEEP_MAX_LEAF"])
+        if os.environ.get("SWEEP_SAH_TRAVERSE"):
+            bp.traverse_cost = float(os.environ["SWEEP_SAH_TRAVERSE"])
     scene = dev.scene(tris, mats, bp)
+    print("scene:", scene.info(), flush=True)
     w, h = wl["width"], wl["height"]
     frame = dev.buffer(w * h * 16)
     ref = None
@@ -40,7 +46,9 @@ def main():
             dev.set_tuning(k, 0)
         for k, v in knobs:
             dev.set_tuning(k, v)
-        p = pt.default_params(width=w, height=h, mode=wl["mode"], accum=pt.ACCUM_LINEAR, first_frame=0, n_frames=frames)
+        integ = {"": pt.INTEGRATOR_AUTO, "mega": pt.INTEGRATOR_MEGAKERNEL, "wavefront": pt.INTEGRATOR_WAVEFRONT}[os.environ.get("SWEEP_INTEGRATOR", "")]
+        p = pt.default_params(width=w, height=h, mode=wl["mode"], accum=pt.ACCUM_LINEAR, first_frame=0, n_frames=frames, integrator=integ,
+                              frames_per_batch=int(os.environ.get("SWEEP_FPB", "0")))
         if "ao_samples" in wl:
             p.ao_samples = wl["ao_samples"]
         if "max_depth" in wl:
