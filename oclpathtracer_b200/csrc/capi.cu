@@ -687,12 +687,19 @@ static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::Re
                 if (SMALL == ptd::PTD_LARGE && a.tune[4] == 0) sc2.smem_nodes = 0;
                 const size_t smem2 = ptd::scene_smem_bytes(sc2, BVH, SMALL, block) + (a.tune[9] > 0 ? size_t(a.tune[9]) * 1024 : 0);
                 // tune[12] = 1: let ptxas use the registers it wants (7 CTAs per SM on the large-scene form) instead of capping at 64 (8 CTAs)
-                auto k = ptd::k_path_sm<SMALL, STATS, 0>;
+                // the large-scene form without statistics: registers capped at 64 (8 CTAs per SM; tune[12] = 1: uncapped, 9: 56 registers) and
+                // six node visits per vote (tune[14] = 1 | 2 | 4: visits per vote, A/B runs)
+                auto k = ptd::k_path_sm<SMALL, STATS, 0, SMALL == ptd::PTD_LARGE ? 6 : 1>;
                 if constexpr (SMALL == ptd::PTD_LARGE && !STATS) {
-                    if (a.tune[12] != 1) k = ptd::k_path_sm<SMALL, STATS, 8>;
-                    if (a.tune[12] == 9) k = ptd::k_path_sm<SMALL, STATS, 9>;
+                    k = ptd::k_path_sm<SMALL, STATS, 8, 6>;
+                    if (a.tune[12] == 1) k = ptd::k_path_sm<SMALL, STATS, 0, 6>;
+                    if (a.tune[12] == 9) k = ptd::k_path_sm<SMALL, STATS, 9, 6>;
+                    if (a.tune[14] == 1) k = ptd::k_path_sm<SMALL, STATS, 8, 1>;
+                    if (a.tune[14] == 2) k = ptd::k_path_sm<SMALL, STATS, 8, 2>;
+                    if (a.tune[14] == 4) k = ptd::k_path_sm<SMALL, STATS, 8, 4>;
                 }
                 if (int rc = set_smem(k, smem2, block, &per_sm)) return rc;
+                if (a.tune[9] < 0 && -a.tune[9] < per_sm) per_sm = -a.tune[9];  // tune[9] = -n: n resident CTAs per SM (latency-sensitivity measurements)
                 long long grid = (long long)per_sm * dev->prop.multiProcessorCount;
                 if (grid > need) grid = need;
                 k<<<(unsigned)grid, block, smem2, dev->stream>>>(sc2, a, work);
