@@ -708,6 +708,8 @@ static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::Re
             }
         }
         auto k = ptd::k_mega_path_regen<BVH, SMALL, STATS>;
+        // FLAT scenes pool the triangle tests of a warp (flat_mt_coop); tune[13] = 2: every lane loops over its own candidates (A/B runs)
+        if constexpr (BVH && SMALL == ptd::PTD_FLAT) if (a.tune[13] != 2) k = ptd::k_mega_path_regen<BVH, SMALL, STATS, true>;
         if (int rc = set_smem(k, smem, block, &per_sm)) return rc;
         long long grid = (long long)per_sm * dev->prop.multiProcessorCount;
         if (grid > need) grid = need;

@@ -96,6 +96,8 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
     c.lstack = nullptr;
     c.ld256 = sc.ld256;
     c.flat_n = sc.flat_n;
+    // FLAT scenes have no traversal stack: the area after the staged records is the warps' scratch for flat_mt_coop
+    c.s_coop = (BVH && SMALL == PTD_FLAT) ? smem_u32(s_stack) + (threadIdx.x >> 5) * (uint32_t)flat_coop_bytes_per_warp(sc.n_tris) : 0u;
     return c;
 }
 
@@ -105,6 +107,7 @@ static inline size_t scene_smem_bytes(const SceneDev& sc, bool bvh, int small, i
     if (bvh) b += small == PTD_FLAT ? (size_t)sc.flat_n * 32 : (size_t)sc.smem_nodes * (small ? 128 : 64);
     if (small) b += (size_t)sc.n_tris * 48 + (size_t)sc.n_mats * 32;
     if (bvh && small != PTD_FLAT && !sc.lstack) b += (size_t)sc.stack_depth * block * 12;  // closest-hit pairs (8 B) + any-hit references (4 B)
+    if (bvh && small == PTD_FLAT) b += (size_t)(block / 32) * (PTD_COOP_FIXED_BYTES + (((size_t)sc.n_tris * 64 + 15) & ~size_t(15)));  // flat_mt_coop scratch per warp
     return b + scratch_per_thread * block;
 }
 
@@ -374,9 +377,11 @@ __global__ void __launch_bounds__(128, ((MODE == PTB_MODE_AO || MODE == PTB_MODE
 // on average).  Here the grid is persistent and a lane whose path ended immediately draws the next sample
 // slot from a global counter (one warp-aggregated atomicAdd per refill), so every warp iteration is one
 // path segment for (nearly) 32 live lanes.  Per-sample arithmetic is unchanged -> identical results.
-template <bool BVH, int SMALL, bool STATS>
-__global__ void __launch_bounds__(128) k_mega_path_regen(const SceneDev sc, const RenderArgs a,
+// COOP (FLAT scenes only): the triangle phase of the query is pooled over the warp (flat_mt_coop)
+template <bool BVH, int SMALL, bool STATS, bool COOP = false>
+__global__ void __launch_bounds__(128, (COOP && !STATS) ? 9 : 0) k_mega_path_regen(const SceneDev sc, const RenderArgs a,
                                                          unsigned long long* work_counter) {
+    static_assert(!COOP || (BVH && SMALL == PTD_FLAT), "the pooled triangle phase belongs to the FLAT query");
     extern __shared__ __align__(16) unsigned char smem[];
     Ctx c = stage_scene<BVH, SMALL>(sc, smem);
     uint2 lstack_mem[PTD_LSTACK_ENTRIES];
@@ -424,8 +429,28 @@ __global__ void __launch_bounds__(128) k_mega_path_regen(const SceneDev sc, cons
             }
         }
         if (!__any_sync(0xffffffffu, alive)) break;
+        Hit ch;  // COOP (FLAT scenes): the query runs warp-cooperatively -- all lanes enter --, then the live lanes shade
+        bool chit = false;
+        uint32_t cvisits = 0;
+        if constexpr (COOP) {
+            unsigned long long tm = 0ull;
+            const uint32_t v0 = qs.visits;
+            if (alive) tm = flat_boxes<STATS>(c, r.o, r.d, 1e20f, qs);
+            cvisits = qs.visits - v0;
+            const unsigned long long key = flat_mt_coop<false>(c, c.s_coop, alive, r.o, r.d, 1e20f, tm, ch.u, ch.v);
+            if (STATS) qs.tests += (uint32_t)__popcll(tm);
+            chit = alive && key != ~0ull;
+            ch.t = __uint_as_float((uint32_t)(key >> 32));
+            ch.pos = (int)(key & 255u); ch.idx = chit ? (int)((key >> 8) & 0xffffffu) : -1;
+        }
         if (alive) {
-            const bool more = path_segment<BVH, SMALL, STATS>(c, r, seed, radiance, mask, depth, a.max_depth, st, rc, qs);
+            bool more;
+            if constexpr (COOP) {
+                rc.closest++;
+                more = path_after_hit<SMALL, STATS>(c, chit, ch, r, seed, radiance, mask, depth, a.max_depth, st, cvisits);
+            } else {
+                more = path_segment<BVH, SMALL, STATS>(c, r, seed, radiance, mask, depth, a.max_depth, st, rc, qs);
+            }
             ++depth;
             if (!more || depth >= a.max_depth) {
                 a.samples[slot] = make_float4(cl_max(radiance.x, 0.0f), cl_max(radiance.y, 0.0f), cl_max(radiance.z, 0.0f), 1.0f);  // :260
