@@ -551,11 +551,11 @@ def main():
     if rank == 0 and wl.get("tess"):
         # Scene traversed from L2/HBM.  Three lines, all <= 1 (profiles/ncu_traffic.json holds the per-ray counts of the committed
         # `ncu --set full` capture of this kernel; the rate is measured live with CUDA events):
-        #   top level = the L1 data pipe: every lane of a node visit reads its own 64-byte record -- two L1 wavefronts per lane and visit --
+        #   top level = the L1 data pipe: every lane of a node visit reads its own 32-byte record -- one L1 wavefront per lane and visit --
         #               and the pipe retires one wavefront per clock and SM; this is the unit closest to saturation, so it is `bound`;
         #   hbm       = the contract's HBM line from the DRAM bytes ncu measured (the tree's cold levels and the triangles);
-        #   l2        = SURVEY 8d's algorithmic bytes per ray (nodes*64 + tri_tests*48 + 16 B/sample: the L1/L2 stream) against the L2 cap.
-        alg = simt["nodes_per_ray"] * 64 + simt["tri_tests_per_ray"] * 48 + 16.0 * job.npix * job.spp / max(1.0, rays_all / args.steps)
+        #   l2        = SURVEY 8d's algorithmic bytes per ray (nodes*32 + tri_tests*48 + 16 B/sample: the L1/L2 stream) against the L2 cap.
+        alg = simt["nodes_per_ray"] * 32 + simt["tri_tests_per_ray"] * 48 + 16.0 * job.npix * job.spp / max(1.0, rays_all / args.steps)
         dram = tr.get("dram_bytes_per_ray")
         wpr = tr.get("l1_wavefronts_per_ray")
         rate = rays_per_launch / (integ_ms * 1e-3)
@@ -567,7 +567,7 @@ def main():
                      "hbm": {"achieved": dram * rate / 1e9 if dram else None, "peak": hbm_peak, "unit": "GB/s", "frac": dram * rate / 1e9 / hbm_peak if dram else None,
                              "dram_bytes_per_ray": dram},
                      "l2": {"algorithmic_bytes_per_ray": alg, "achieved": alg * rate / 1e9, "peak": l2_peak, "unit": "GB/s", "frac": alg * rate / 1e9 / l2_peak,
-                            "note": "SURVEY 8d's algorithmic bytes (nodes*64 + tri_tests*48 + 16 B/sample) are the L1/L2 stream, quoted against the L2 bandwidth cap"},
+                            "note": "SURVEY 8d's algorithmic bytes (nodes*32 [quantised 32-byte records] + tri_tests*48 + 16 B/sample) are the L1/L2 stream, quoted against the L2 bandwidth cap"},
                      "simt": simt,
                      "binding": "the L1 data pipe (ncu: l1tex__data_pipe_lsu_wavefronts at 84 % of peak) together with issue slots at 56 % and long-scoreboard "
                                 "stalls on dependent node fetches; HBM and L2 bandwidth are far from their peaks",

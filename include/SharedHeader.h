@@ -75,6 +75,17 @@ typedef struct ptb_bvh_node {
     int32_t pad1; /* word 3: child-1 half-extent */
 } ptb_bvh_node;
 
+/* Quantised encoding of a binary node, 2 x 128-bit words = 32 B: what the kernels traverse for width-2 scenes (one 256-bit load
+ * per visit instead of two: the L1 data pipe, one wavefront per clock and SM, is what binds the traversal of a scene that lives in
+ * L2/HBM).  Box planes are 16-bit indices on a grid over the scene: plane = grid_lo[axis] + q * grid_step[axis].  The encoding is a
+ * pure function of the ptb_bvh_node array (rules Q1-Q3, csrc/lbvh.cuh: k_quant_grid / k_quant_nodes == the CPU oracle's
+ * ora_bvh_quantize): every quantised box contains its fp32 box with a full grid step to spare.  Node numbering = ptb_bvh_node's. */
+typedef struct ptb_bvh_nodeq {
+    uint32_t box0[3]; /* child 0: x, y, z words, each lo plane | hi plane << 16 */
+    uint32_t box1[3]; /* child 1 */
+    int32_t child0, child1;
+} ptb_bvh_nodeq;
+
 typedef struct ptb_bvh_node4 {
     float c0[3];
     int32_t child0; /* word 0: child-0 centre,      child-0 ref */
@@ -194,6 +205,7 @@ typedef struct ptb_counters {
 static_assert(sizeof(ptb_material) == 64, "Material must be 64 bytes (RaytraceTest.cpp:50-59)");
 static_assert(sizeof(ptb_triangle) == 64, "Triangle must be 64 bytes (RaytraceTest.cpp:61-76)");
 static_assert(sizeof(ptb_bvh_node) == 64, "binary BVH node must be 64 bytes");
+static_assert(sizeof(ptb_bvh_nodeq) == 32, "quantised binary BVH node must be 32 bytes");
 static_assert(sizeof(ptb_bvh_node4) == 128, "4-wide BVH node must be 128 bytes");
 static_assert(sizeof(ptb_bvh_tri) == 48, "BVH triangle must be 48 bytes");
 static_assert(sizeof(ptb_bvh_leafbox) == 32, "flat leaf box must be 32 bytes");

@@ -157,13 +157,17 @@ int ptb_scene_create_gpu(ptb_device* dev, const ptb_triangle* tris, int n_tris, 
 int ptb_scene_destroy(ptb_scene* scene);
 int ptb_scene_info(ptb_scene* scene, int* n_nodes, int* n_tris, int* depth, int* smem_nodes);
 /* form of the resident scene: 1 (FLAT: ptb_bvh_leafbox records, scenes of <= 32 leaves and <= 64 triangles), 4
- * (ptb_bvh_node4, scenes that fit a 32 KB shared-memory budget) or 2 (ptb_bvh_node, traversed from L2/HBM) */
+ * (ptb_bvh_node4, scenes that fit a 32 KB shared-memory budget) or 2 (binary ptb_bvh_node, traversed from L2/HBM through
+ * its quantised encoding ptb_bvh_nodeq) */
 int ptb_scene_bvh_width(ptb_scene* scene);
 /* form a render of `mode` (PTB_MODE_*) walks: a FLAT scene keeps its 4-wide tree resident too and uses it where the rays of a
  * warp are coherent (PTB_MODE_DIRECT); results are identical, the visit statistics follow the form */
 int ptb_scene_mode_width(ptb_scene* scene, int mode);
 /* host copies of the built tree (n_nodes records of the scene's width), for structural validation and tests */
 int ptb_scene_copy_bvh(ptb_scene* scene, void* nodes, int32_t* tri_order);
+/* width-2 scenes: the 32-byte quantised encoding of the binary tree that the kernels traverse (ptb_bvh_nodeq, n_nodes records)
+ * and its grid (SharedHeader.h); qnodes may be NULL to fetch the grid only */
+int ptb_scene_copy_bvh_quantized(ptb_scene* scene, uint32_t* qnodes, float grid_lo[3], float grid_step[3]);
 
 /* ---- the hot path -------------------------------------------------------------------
  * per-pixel statistics of the LAST frame of a call (collect_stats = 1)          */

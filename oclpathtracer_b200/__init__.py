@@ -96,7 +96,7 @@ EXPORTS = [
     "ptb_buffer_map", "ptb_buffer_unmap", "ptb_buffer_clear", "ptb_buffer_device_ptr", "ptb_buffer_mark_dirty", "ptb_buffer_size",
     "ptb_kernel_get", "ptb_kernel_set_int", "ptb_launch1d", "ptb_launch_serialize", "ptb_launch_deserialize", "ptb_load_model", "ptb_tessellate",
     "ptb_light_from_quad", "ptb_free", "ptb_to_rgb8", "ptb_write_ppm", "ptb_bvh_params_default",
-    "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_create_gpu", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_bvh_width", "ptb_scene_mode_width", "ptb_scene_copy_bvh",
+    "ptb_bvh_build_host", "ptb_scene_create", "ptb_scene_create_gpu", "ptb_scene_destroy", "ptb_scene_info", "ptb_scene_bvh_width", "ptb_scene_mode_width", "ptb_scene_copy_bvh", "ptb_scene_copy_bvh_quantized",
     "ptb_render_params_default", "ptb_render_local_pixels", "ptb_render", "ptb_render_host",
     "ptb_buffer_ipc_export", "ptb_buffer_ipc_import", "ptb_render_gather",
     "ptb_render_host_async", "ptb_job_wait", "ptb_host_alloc", "ptb_host_free", "ptb_trace",
@@ -141,6 +141,7 @@ def lib():
         L.ptb_bvh_build_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6
         L.ptb_scene_bvh_width.argtypes = [C.c_void_p]
         L.ptb_scene_mode_width.argtypes = [C.c_void_p, C.c_int]
+        L.ptb_scene_copy_bvh_quantized.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ptb_device_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ptb_device_add_helper.argtypes = [C.c_void_p, C.c_void_p]
         L.ptb_device_helper_count.argtypes = [C.c_void_p]
@@ -603,6 +604,13 @@ class Scene:
         order = np.zeros(inf["n_tris"], np.int32)
         _check(lib().ptb_scene_copy_bvh(self._h, _p(nodes), _p(order)))
         return nodes, order
+
+    def bvh_quantized(self):
+        """width-2 scenes: (uint32[n_nodes, 8] quantised records the kernels traverse, grid lo[3], grid step[3])"""
+        q = np.zeros((self.info()["n_nodes"], 8), np.uint32)
+        lo, step = (C.c_float * 3)(), (C.c_float * 3)()
+        _check(lib().ptb_scene_copy_bvh_quantized(self._h, _p(q), lo, step))
+        return q, [float(x) for x in lo], [float(x) for x in step]
 
     def close(self):
         if self._h:

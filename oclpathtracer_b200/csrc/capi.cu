@@ -126,6 +126,8 @@ struct ptb_scene {
     const BuiltBvh& built() const { return *bvhp; }
     int n_tris = 0, n_mats = 0;
     float4* d_nodes = nullptr;
+    uint4* d_nodesq = nullptr;            // binary scenes: the 32-byte quantised encoding of d_nodes that the kernels traverse (ptb_bvh_nodeq)
+    float q_lo[3] = {0, 0, 0}, q_step[3] = {1, 1, 1};  // its grid
     float4* d_nodes4 = nullptr;           // FLAT scenes also keep their 4-wide tree resident: coherent-ray modes use it (mode_class)
     float4* d_tris = nullptr;
     float4* d_tris_orig = nullptr;
@@ -401,9 +403,29 @@ extern "C" int ptb_scene_destroy(ptb_scene* s) {
     if (!s) return PTB_OK;
     set_device(s->dev);
     cudaStreamSynchronize(s->dev->stream);
-    for (void* p : {(void*)s->d_nodes, (void*)s->d_nodes4, (void*)s->d_tris, (void*)s->d_tris_orig, (void*)s->d_mats, (void*)s->d_order})
+    for (void* p : {(void*)s->d_nodes, (void*)s->d_nodesq, (void*)s->d_nodes4, (void*)s->d_tris, (void*)s->d_tris_orig, (void*)s->d_mats, (void*)s->d_order})
         if (p) cudaFree(p);
     delete s;
+    return PTB_OK;
+}
+
+// Binary trees are traversed through their quantised encoding: derive it on the device from the fp32 nodes (lbvh.cuh:
+// k_quant_grid / k_quant_nodes) and fetch the six grid numbers the kernels take as parameters.
+static int quantize_scene(ptb_scene* s) {
+    ptb_device* dev = s->dev;
+    float* d_grid = nullptr;
+    CU_TRY(cudaMalloc((void**)&s->d_nodesq, size_t(s->n_nodes) * 32));
+    CU_TRY(cudaMalloc((void**)&d_grid, 6 * sizeof(float)));
+    ptd::k_quant_grid<<<1, 32, 0, dev->stream>>>(s->d_nodes, d_grid);
+    ptd::k_quant_nodes<<<(unsigned)((s->n_nodes + 255) / 256), 256, 0, dev->stream>>>(s->d_nodes, s->n_nodes, d_grid, s->d_nodesq);
+    float grid[6];
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(grid, d_grid, sizeof grid, cudaMemcpyDeviceToHost, dev->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dev->stream);
+    cudaFree(d_grid);
+    if (e != cudaSuccess) return fail(PTB_E_CUDA, "ptb_scene_create: node quantisation failed: %s", cudaGetErrorString(e));
+    for (int a = 0; a < 3; ++a) { s->q_lo[a] = grid[a]; s->q_step[a] = grid[3 + a]; }
+    dev->kernel_launches += 2;
     return PTB_OK;
 }
 
@@ -471,6 +493,8 @@ static int scene_create_impl(ptb_device* dev, const ptb_triangle* tris, int n_tr
         ptb_scene_destroy(s);
         return fail(PTB_E_CUDA, "ptb_scene_create: upload failed: %s", cudaGetErrorString(e));
     }
+    if (s->cls == ptd::PTD_LARGE)
+        if ((rc = quantize_scene(s))) { ptb_scene_destroy(s); return rc; }
     *out = s;
     return PTB_OK;
 }
@@ -527,6 +551,7 @@ extern "C" int ptb_scene_create_gpu(ptb_device* dev, const ptb_triangle* tris, i
     };
     if ((rc = up(&s->d_tris_orig, orig.data(), orig.size() * 48)) || (rc = up(&s->d_mats, m.data(), m.size() * 16))) return fail_out(rc);
     if (cudaStreamSynchronize(dev->stream) != cudaSuccess) return fail_out(fail(PTB_E_CUDA, "ptb_scene_create_gpu: sync failed"));
+    if ((rc = quantize_scene(s))) return fail_out(rc);
     cudaFree(d_raw);
     *out = s;
     return PTB_OK;
@@ -578,6 +603,21 @@ extern "C" int ptb_scene_info(ptb_scene* s, int* n_nodes, int* n_tris, int* dept
 
 extern "C" int ptb_scene_bvh_width(ptb_scene* s) { return s ? s->width : 0; }
 
+extern "C" int ptb_scene_copy_bvh_quantized(ptb_scene* s, uint32_t* qnodes, float grid_lo[3], float grid_step[3]) {
+    if (!s) return fail(PTB_E_INVALID, "ptb_scene_copy_bvh_quantized: null scene");
+    if (!s->d_nodesq) return fail(PTB_E_INVALID, "ptb_scene_copy_bvh_quantized: the scene has no binary tree (width %d)", s->width);
+    if (set_device(s->dev)) return PTB_E_CUDA;
+    if (qnodes) {
+        CU_TRY(cudaMemcpyAsync(qnodes, s->d_nodesq, size_t(s->n_nodes) * 32, cudaMemcpyDeviceToHost, s->dev->stream));
+        CU_TRY(cudaStreamSynchronize(s->dev->stream));
+    }
+    for (int a = 0; a < 3; ++a) {
+        if (grid_lo) grid_lo[a] = s->q_lo[a];
+        if (grid_step) grid_step[a] = s->q_step[a];
+    }
+    return PTB_OK;
+}
+
 extern "C" int ptb_scene_copy_bvh(ptb_scene* s, void* nodes, int32_t* tri_order) {
     if (!s) return fail(PTB_E_INVALID, "ptb_scene_copy_bvh: null scene");
     if (!s->host_copy_valid) {  // GPU-built tree: download on first request
@@ -615,7 +655,9 @@ extern "C" int ptb_scene_mode_width(ptb_scene* s, int mode) {
 
 static ptd::SceneDev scene_dev(const ptb_scene* s, int cls) {
     ptd::SceneDev d;
-    d.nodes = s->d_nodes; d.tris = s->d_tris; d.tris_orig = s->d_tris_orig; d.mats = s->d_mats;
+    d.nodes = s->cls == ptd::PTD_LARGE ? reinterpret_cast<const float4*>(s->d_nodesq) : s->d_nodes;
+    d.tris = s->d_tris; d.tris_orig = s->d_tris_orig; d.mats = s->d_mats;
+    for (int a = 0; a < 3; ++a) { d.q_lo[a] = s->q_lo[a]; d.q_step[a] = s->q_step[a]; }
     d.n_nodes = s->n_nodes; d.n_tris = s->n_tris; d.n_mats = s->n_mats;
     if (cls == ptd::PTD_SMALL4 && s->cls == ptd::PTD_FLAT) {  // the resident 4-wide tree of a FLAT scene
         d.nodes = s->d_nodes4; d.n_nodes = int(s->built().nodes4.size());

@@ -241,4 +241,57 @@ cleanup:
     return rc;
 }
 
+// ---- quantised encoding of a binary tree (ptb_bvh_nodeq; DESIGN.md section 4 "Quantised binary nodes") ----------------
+// A pure function of the fp32 node array, evaluated on the device for host-built and device-built trees alike; the CPU
+// oracle re-states it (ora_bvh_quantize, rules Q1-Q3) and the tests compare the bytes.  IEEE double, no
+// contraction (--fmad=false).
+// grid[0..2] = q_lo, grid[3..5] = q_step from the ROOT's child boxes (rule Q1)
+__global__ void k_quant_grid(const float4* nodes, float* grid) {
+    if (blockIdx.x || threadIdx.x) return;
+    const float4 n0 = nodes[0], n1 = nodes[1], n2 = nodes[2], n3 = nodes[3];
+    const float c[2][3] = {{n0.x, n0.y, n0.z}, {n2.x, n2.y, n2.z}};
+    const float e[2][3] = {{n1.x, n1.y, n1.z}, {n3.x, n3.y, n3.z}};
+    const int refs[2] = {__float_as_int(n0.w), __float_as_int(n1.w)};
+    for (int a = 0; a < 3; ++a) {
+        double lo = 0.0, hi = 0.0;
+        bool have = false;
+        for (int k = 0; k < 2; ++k) {
+            if (refs[k] == PTB_BVH_EMPTY) continue;
+            const double l = (double)c[k][a] - (double)e[k][a], h = (double)c[k][a] + (double)e[k][a];
+            if (!have || l < lo) lo = l;
+            if (!have || h > hi) hi = h;
+            have = true;
+        }
+        double ext = hi - lo;
+        if (!(ext > 0.0)) ext = 1.0;
+        const double margin = ext / 1024.0;
+        grid[a] = (float)(lo - margin);
+        grid[3 + a] = (float)((ext + 2.0 * margin) / 65000.0);
+    }
+}
+// rules Q2, Q3: one thread per node
+__global__ void __launch_bounds__(256) k_quant_nodes(const float4* nodes, int n_nodes, const float* grid, uint4* q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const float4 n0 = nodes[4 * (size_t)i], n1 = nodes[4 * (size_t)i + 1], n2 = nodes[4 * (size_t)i + 2], n3 = nodes[4 * (size_t)i + 3];
+    const float c[2][3] = {{n0.x, n0.y, n0.z}, {n2.x, n2.y, n2.z}};
+    const float e[2][3] = {{n1.x, n1.y, n1.z}, {n3.x, n3.y, n3.z}};
+    const int refs[2] = {__float_as_int(n0.w), __float_as_int(n1.w)};
+    uint32_t w[6];
+    for (int k = 0; k < 2; ++k)
+        for (int a = 0; a < 3; ++a) {
+            uint32_t ql = 65535u, qh = 0u;
+            if (refs[k] != PTB_BVH_EMPTY) {
+                const double plo = (double)c[k][a] - (double)e[k][a], phi = (double)c[k][a] + (double)e[k][a];
+                const double fl = floor((plo - (double)grid[a]) / (double)grid[3 + a]) - 1.0;
+                const double fh = ceil((phi - (double)grid[a]) / (double)grid[3 + a]) + 1.0;
+                ql = fl < 0.0 ? 0u : fl > 65535.0 ? 65535u : (uint32_t)(long long)fl;
+                qh = fh < 0.0 ? 0u : fh > 65535.0 ? 65535u : (uint32_t)(long long)fh;
+            }
+            w[3 * k + a] = ql | (qh << 16);
+        }
+    q[2 * (size_t)i] = make_uint4(w[0], w[1], w[2], w[3]);
+    q[2 * (size_t)i + 1] = make_uint4(w[4], w[5], (uint32_t)refs[0], (uint32_t)refs[1]);
+}
+
 }  // namespace ptd

@@ -43,7 +43,7 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
     Ctx c;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
     unsigned char* p = smem + 16;
-    const uint32_t node_bytes = !BVH ? 0u : SMALL == PTD_FLAT ? (uint32_t)sc.flat_n * 32u : (uint32_t)sc.smem_nodes * (SMALL ? 128u : 64u);
+    const uint32_t node_bytes = !BVH ? 0u : SMALL == PTD_FLAT ? (uint32_t)sc.flat_n * 32u : (uint32_t)sc.smem_nodes * (SMALL ? 128u : 32u);
     const uint32_t tri_bytes = SMALL ? (uint32_t)sc.n_tris * 48u : 0u;
     const uint32_t mat_bytes = SMALL ? (uint32_t)sc.n_mats * 32u : 0u;
     float4* s_nodes = reinterpret_cast<float4*>(p);
@@ -96,6 +96,7 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
     c.lstack = nullptr;
     c.ld256 = sc.ld256;
     c.flat_n = sc.flat_n;
+    for (int k = 0; k < 3; ++k) { c.q_lo[k] = sc.q_lo[k]; c.q_step[k] = sc.q_step[k]; }
     // FLAT scenes have no traversal stack: the area after the staged records is the warps' scratch for flat_mt_coop
     c.s_coop = (BVH && SMALL == PTD_FLAT) ? smem_u32(s_stack) + (threadIdx.x >> 5) * (uint32_t)flat_coop_bytes_per_warp(sc.n_tris) : 0u;
     return c;
@@ -104,7 +105,7 @@ PTD_FI Ctx stage_scene(const SceneDev& sc, unsigned char* smem) {
 // host helper: bytes of dynamic shared memory for a launch
 static inline size_t scene_smem_bytes(const SceneDev& sc, bool bvh, int small, int block, size_t scratch_per_thread = 0) {
     size_t b = 16;
-    if (bvh) b += small == PTD_FLAT ? (size_t)sc.flat_n * 32 : (size_t)sc.smem_nodes * (small ? 128 : 64);
+    if (bvh) b += small == PTD_FLAT ? (size_t)sc.flat_n * 32 : (size_t)sc.smem_nodes * (small ? 128 : 32);
     if (small) b += (size_t)sc.n_tris * 48 + (size_t)sc.n_mats * 32;
     if (bvh && small != PTD_FLAT && !sc.lstack) b += (size_t)sc.stack_depth * block * 12;  // closest-hit pairs (8 B) + any-hit references (4 B)
     if (bvh && small == PTD_FLAT) b += (size_t)(block / 32) * (PTD_COOP_FIXED_BYTES + (((size_t)sc.n_tris * 64 + 15) & ~size_t(15)));  // flat_mt_coop scratch per warp
@@ -488,22 +489,20 @@ __global__ void __launch_bounds__(128, (COOP && !STATS) ? 9 : 0) k_mega_path_reg
 // States are one-hot BYTES of one word, so that ONE warp reduction (REDUX.SUM) counts the lanes of all states at once.
 enum : uint32_t { ST_DONE = 0u, ST_REGEN = 1u, ST_NODE = 1u << 8, ST_LEAF = 1u << 16, ST_SHADE = 1u << 24 };
 
-// Visit of a BINARY node from global memory with the stack in local memory (the 2M-triangle scene's form).  Same rule as
-// node_step2 (DESIGN.md "Traversal order") with the common outcomes free of divergent paths: every lane fetches its node
-// and, speculatively, its stack top together; descend / push / pop-of-a-live-entry are selects and one predicated store.
-// Only a pop that meets culled entries (entry distance > best_t) loops.  False = the query finished.
+// Visit of a (quantised) BINARY node from global memory with the stack in local memory (the 2M-triangle scene's form).  Same
+// rule as node_step2 (DESIGN.md "Traversal order") with the common outcomes free of divergent paths: every lane fetches its node
+// with ONE 256-bit load and, speculatively, its stack top together; descend / push / pop-of-a-live-entry are selects and one
+// predicated store.  Only a pop that meets culled entries (entry distance > best_t) loops.  False = the query finished.
 template <bool STATS>
-PTD_FI bool node_step2_bf(const Ctx& c, V3 invd, V3 ood, float best_t, int& cur, int& sp, QueryStats& qs) {
-    const float4* p = c.g_nodes + 4 * (size_t)cur;
-    float4 n0, n1, n2, n3;
-    ldg256(p, n0, n1); ldg256(p + 2, n2, n3);
+PTD_FI bool node_step2_bf(const Ctx& c, const RayPre& rp, float best_t, int& cur, int& sp, QueryStats& qs) {
+    uint4 a, b;
+    ldg_nodeq(c.g_nodes, cur, a, b);
     const uint2 top = c.lstack[sp > 0 ? sp - 1 : 0];
     if (STATS) qs.visits++;
     float tn0, tn1;
-    const V3 ainv = mk(fabsf(invd.x), fabsf(invd.y), fabsf(invd.z));
-    const bool h0 = slab(xyz(n0), xyz(n1), invd, ainv, ood, best_t, tn0);
-    const bool h1 = slab(xyz(n2), xyz(n3), invd, ainv, ood, best_t, tn1);
-    const int c0 = __float_as_int(n0.w), c1 = __float_as_int(n1.w);
+    const bool h0 = qslab(a.x, a.y, a.z, rp, best_t, tn0);
+    const bool h1 = qslab(a.w, b.x, b.y, rp, best_t, tn1);
+    const int c0 = (int)b.z, c1 = (int)b.w;
     const bool second_first = tn1 < tn0;
     const bool both = h0 && h1;
     if (both) c.lstack[sp] = make_uint2((uint32_t)(second_first ? c0 : c1), __float_as_uint(second_first ? tn0 : tn1));
@@ -535,7 +534,7 @@ __global__ void __launch_bounds__(128, MINB) k_path_sm(const SceneDev sc, const 
     const long long total = (long long)a.frames_in_batch * a.n_local;
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t thr_regen = a.tune[0] > 0 ? a.tune[0] : 6;
-    const uint32_t thr_shade = a.tune[10] > 0 ? a.tune[10] : 12;
+    const uint32_t thr_shade = a.tune[10] > 0 ? a.tune[10] : 16;
     const uint32_t thr_leaf = a.tune[11] > 0 ? a.tune[11] : 10;
     RayCount rc{0u, 0u};
     QueryStats qs{0u, 0u};
@@ -547,7 +546,7 @@ __global__ void __launch_bounds__(128, MINB) k_path_sm(const SceneDev sc, const 
     Ray r{mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 1.f)};
     V3 radiance = mk(0.f, 0.f, 0.f), mask = mk(1.f, 1.f, 1.f);
     // query state
-    V3 invd = mk(0.f, 0.f, 0.f), ood = invd;
+    RayPre rp{mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 0.f), {0u, 0u, 0u}};
     float best_t = 1e20f, best_u = 0.f, best_v = 0.f;
     int best_pos = -1, best_idx = -1, cur = 0, sp = 0;
     unsigned long long tm = 0ull;  // FLAT: triangles still to test
@@ -556,8 +555,7 @@ __global__ void __launch_bounds__(128, MINB) k_path_sm(const SceneDev sc, const 
         visits0 = qs.visits;
         best_t = 1e20f; best_u = best_v = 0.f; best_pos = best_idx = -1;
         if constexpr (SMALL != PTD_FLAT) {
-            invd = safe_rcp3(r.d);
-            ood = mk(r.o.x * invd.x, r.o.y * invd.y, r.o.z * invd.z);
+            rp = ray_pre<SMALL>(c, r.o, r.d);
             cur = 0; sp = 0;
         }
         state = ST_NODE;
@@ -605,12 +603,12 @@ __global__ void __launch_bounds__(128, MINB) k_path_sm(const SceneDev sc, const 
                         // NSTEP visits per vote (a lane that reaches a leaf or ends its query sits the rest out): the vote and its
                         // dispatch are a quarter of a single-visit iteration.  C5: 1 -> 3.73, 2 -> 3.95, 4 -> 4.08, 6 -> 4.11, 8 -> 3.96 Grays/s;
                         // re-voting adaptively (while 5/8..7/8 of the lanes are still at a node) measured 3.86..3.99.
-                        more = node_step2_bf<STATS>(c, invd, ood, best_t, cur, sp, qs);
+                        more = node_step2_bf<STATS>(c, rp, best_t, cur, sp, qs);
 #pragma unroll
                         for (int rep = 1; rep < NSTEP; ++rep)
-                            if (more && cur >= 0) more = node_step2_bf<STATS>(c, invd, ood, best_t, cur, sp, qs);
+                            if (more && cur >= 0) more = node_step2_bf<STATS>(c, rp, best_t, cur, sp, qs);
                     }
-                    else more = node_step<false, SMALL, STATS>(c, invd, ood, best_t, cur, sp, qs);
+                    else more = node_step<false, SMALL, STATS>(c, rp, best_t, cur, sp, qs);
                     state = !more ? ST_SHADE : cur >= 0 ? ST_NODE : ST_LEAF;
                 }
             }

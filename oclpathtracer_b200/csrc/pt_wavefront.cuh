@@ -126,7 +126,8 @@ PTD_FI void trace_persistent(const Ctx& c, IO& io, const unsigned int n_rays, un
     bool active = false;
     bool exhausted = false;  // warp-uniform
     unsigned int idx = 0;
-    V3 o = mk(0.f, 0.f, 0.f), d = o, invd = o, ood = o;
+    V3 o = mk(0.f, 0.f, 0.f), d = o;
+    RayPre rp{o, o, {0u, 0u, 0u}};
     float best_t = 0.f, best_u = 0.f, best_v = 0.f;
     int best_pos = -1, best_idx = -1, cur = 0, sp = 0;
     QueryStats qs{0u, 0u};
@@ -141,8 +142,7 @@ PTD_FI void trace_persistent(const Ctx& c, IO& io, const unsigned int n_rays, un
                 idx = base + (unsigned int)__popc(idle & ((1u << lane) - 1u));
                 float tmax;
                 if (idx < n_rays && io.load(idx, o, d, tmax)) {
-                    invd = safe_rcp3(d);
-                    ood = mk(o.x * invd.x, o.y * invd.y, o.z * invd.z);
+                    rp = ray_pre<SMALL>(c, o, d);
                     best_t = tmax; best_u = best_v = 0.f; best_pos = best_idx = -1;
                     cur = 0; sp = 0;
                     qs.visits = qs.tests = 0u;
@@ -161,7 +161,7 @@ PTD_FI void trace_persistent(const Ctx& c, IO& io, const unsigned int n_rays, un
             bool fin = false, blocked = false;
             Hit h;
             while (active && !fin && cur >= 0)
-                if (!node_step<ANY, SMALL, STATS>(c, invd, ood, best_t, cur, sp, qs)) fin = true;
+                if (!node_step<ANY, SMALL, STATS>(c, rp, best_t, cur, sp, qs)) fin = true;
             if (active && !fin) {  // leaf
                 const uint32_t code = (uint32_t)(~cur);
                 const int first = (int)(code >> 3), count = (int)(code & 7u) + 1;
@@ -206,7 +206,8 @@ PTD_FI void trace_persistent_sm(const Ctx& c, IO& io, const unsigned int n_rays,
     uint32_t state = ST_REGEN;  // ST_REGEN = idle: the lane wants a ray
     bool exhausted = false;     // warp-uniform
     unsigned int idx = 0;
-    V3 o = mk(0.f, 0.f, 0.f), d = o, invd = o, ood = o;
+    V3 o = mk(0.f, 0.f, 0.f), d = o;
+    RayPre rp{o, o, {0u, 0u, 0u}};
     float best_t = 0.f, best_u = 0.f, best_v = 0.f;
     int best_pos = -1, best_idx = -1, cur = 0, sp = 0;
     bool blocked = false;
@@ -233,8 +234,7 @@ PTD_FI void trace_persistent_sm(const Ctx& c, IO& io, const unsigned int n_rays,
                 idx = base + (unsigned int)__popc(idle & ((1u << lane) - 1u));
                 float tmax;
                 if (idx < n_rays && io.load(idx, o, d, tmax)) {
-                    invd = safe_rcp3(d);
-                    ood = mk(o.x * invd.x, o.y * invd.y, o.z * invd.z);
+                    rp = ray_pre<SMALL>(c, o, d);
                     best_t = tmax; best_u = best_v = 0.f; best_pos = best_idx = -1;
                     cur = 0; sp = 0; blocked = false;
                     qs.visits = qs.tests = 0u;
@@ -270,8 +270,8 @@ PTD_FI void trace_persistent_sm(const Ctx& c, IO& io, const unsigned int n_rays,
         if (!n_node) break;  // nobody walks and the idle lanes cannot be refilled
         if (state == ST_NODE) {
             bool more;
-            if (!ANY && SMALL == PTD_LARGE && fast_nodes) more = node_step2_bf<STATS>(c, invd, ood, best_t, cur, sp, qs);
-            else more = node_step<ANY, SMALL, STATS>(c, invd, ood, best_t, cur, sp, qs);
+            if (!ANY && SMALL == PTD_LARGE && fast_nodes) more = node_step2_bf<STATS>(c, rp, best_t, cur, sp, qs);
+            else more = node_step<ANY, SMALL, STATS>(c, rp, best_t, cur, sp, qs);
             if (!more) finish();
             else state = cur >= 0 ? ST_NODE : ST_LEAF;
         }

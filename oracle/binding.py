@@ -55,6 +55,7 @@ class Bvh(C.Structure):
     _fields_ = [
         ("nodes", C.c_void_p), ("n_nodes", C.c_int32),
         ("tri_order", C.c_void_p), ("n_tris", C.c_int32), ("width", C.c_int32),
+        ("qnodes", C.c_void_p), ("q_lo", C.c_float * 3), ("q_step", C.c_float * 3),
     ]
 
 
@@ -174,13 +175,30 @@ def generate_ray(gi, gj, w, h, seed):
     return np.array(o, np.float32), np.array(d, np.float32), s.value
 
 
-def make_bvh(nodes, tri_order):
+def make_bvh(nodes, tri_order, quantized=True):
     """nodes: NODE_DTYPE (binary) or NODE4_DTYPE (4-wide) array; tri_order: int32 array.  Returns (Bvh, keepalive)."""
     nodes = np.ascontiguousarray(nodes)
     order = np.ascontiguousarray(tri_order, np.int32)
     width = {64: 2, 128: 4, 32: 1}[nodes.dtype.itemsize]
     b = Bvh(nodes.ctypes.data, len(nodes), order.ctypes.data, len(order), width)
-    return b, (nodes, order)
+    keep = [nodes, order]
+    if width == 2 and quantized:  # the product traverses binary trees through their quantised encoding (ptb_bvh_nodeq)
+        q, lo, step = quantize(nodes)
+        b.qnodes = q.ctypes.data
+        b.q_lo[:] = lo
+        b.q_step[:] = step
+        keep.append(q)
+    return b, tuple(keep)
+
+
+def quantize(nodes):
+    """ora_bvh_quantize: (uint32[n, 8] quantised records, grid lo[3], grid step[3]) of a binary tree"""
+    nodes = np.ascontiguousarray(nodes)
+    q = np.zeros((len(nodes), 8), np.uint32)
+    lo, step = (C.c_float * 3)(), (C.c_float * 3)()
+    if lib().ora_bvh_quantize(_p(nodes), len(nodes), _p(q), lo, step) != 0:
+        raise RuntimeError("ora_bvh_quantize failed")
+    return q, [float(x) for x in lo], [float(x) for x in step]
 
 
 def bvh_params(**kw):

@@ -397,3 +397,54 @@ int ora_bvh_build(const ora_triangle* tris, int n_tris, const ora_bvh_params* pa
     free(B.prims); free(B.nodes);
     return rc;
 }
+
+/* Quantised binary nodes.  Rules, all in IEEE double unless stated:
+ *  Q1 grid: per axis lo = min, hi = max over the ROOT's non-empty child boxes of (double)c -/+ (double)e; ext = hi - lo
+ *     (1.0 when not positive); margin = ext / 1024; q_lo = (float)(lo - margin); q_step = (float)((ext + 2 * margin) / 65000).
+ *  Q2 plane indices of a child box: ql = floor(((double)c - (double)e - (double)q_lo) / (double)q_step) - 1,
+ *     qh = ceil(((double)c + (double)e - (double)q_lo) / (double)q_step) + 1, both clamped to [0, 65535]; an EMPTY child
+ *     gets ql = 65535, qh = 0 (never hit).  The quantised box contains the fp32 box with a full grid step to spare on
+ *     each side, which covers the half step the fp32 plane-distance formula of the traversal can be off by.
+ *  Q3 record: words 0..2 = child 0 (x, y, z: ql | qh << 16), words 3..5 = child 1, words 6, 7 = the child references. */
+int ora_bvh_quantize(const ora_bvh_node* nodes, int n_nodes, uint32_t* q_out, float q_lo[3], float q_step[3]) {
+    if (!nodes || n_nodes < 1 || !q_out) return -1;
+    for (int a = 0; a < 3; a++) {
+        double lo = 0.0, hi = 0.0;
+        int have = 0;
+        const float* cs[2] = {nodes[0].c0, nodes[0].c1};
+        const float* es[2] = {nodes[0].e0, nodes[0].e1};
+        const int32_t refs[2] = {nodes[0].child0, nodes[0].child1};
+        for (int k = 0; k < 2; k++) {
+            if (refs[k] == ORA_EMPTY) continue;
+            const double l = (double)cs[k][a] - (double)es[k][a], h = (double)cs[k][a] + (double)es[k][a];
+            if (!have || l < lo) lo = l;
+            if (!have || h > hi) hi = h;
+            have = 1;
+        }
+        double ext = hi - lo;
+        if (!(ext > 0.0)) ext = 1.0;
+        const double margin = ext / 1024.0;
+        q_lo[a] = (float)(lo - margin);
+        q_step[a] = (float)((ext + 2.0 * margin) / 65000.0);
+    }
+    for (int i = 0; i < n_nodes; i++) {
+        const float* cs[2] = {nodes[i].c0, nodes[i].c1};
+        const float* es[2] = {nodes[i].e0, nodes[i].e1};
+        const int32_t refs[2] = {nodes[i].child0, nodes[i].child1};
+        for (int k = 0; k < 2; k++)
+            for (int a = 0; a < 3; a++) {
+                long ql = 65535, qh = 0;
+                if (refs[k] != ORA_EMPTY) {
+                    const double plo = (double)cs[k][a] - (double)es[k][a], phi = (double)cs[k][a] + (double)es[k][a];
+                    const double fl = floor((plo - (double)q_lo[a]) / (double)q_step[a]) - 1.0;
+                    const double fh = ceil((phi - (double)q_lo[a]) / (double)q_step[a]) + 1.0;
+                    ql = fl < 0.0 ? 0 : fl > 65535.0 ? 65535 : (long)fl;
+                    qh = fh < 0.0 ? 0 : fh > 65535.0 ? 65535 : (long)fh;
+                }
+                q_out[(size_t)i * 8 + (size_t)k * 3 + (size_t)a] = (uint32_t)ql | ((uint32_t)qh << 16);
+            }
+        q_out[(size_t)i * 8 + 6] = (uint32_t)nodes[i].child0;
+        q_out[(size_t)i * 8 + 7] = (uint32_t)nodes[i].child1;
+    }
+    return 0;
+}

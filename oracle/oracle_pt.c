@@ -417,6 +417,39 @@ static inline int bvh_slab(const float c[3], const float e[3], const float invd[
 }
 
 
+/* N4q: BUILD-DEFINED slab test on a QUANTISED box (ora_bvh.qnodes; DESIGN.md section 4 "Quantised binary nodes").  Per ray and
+ * axis A = q_step * invd and B = fma(-2^23, A, fma(q_lo, invd, -(o * invd))); the distance to grid plane q is ONE fma,
+ * t = fma(2^23 + q, A, B), the factor being the float whose bits are 0x4B000000 | q (exact for q < 2^23).  The near plane
+ * of an axis is the lo plane when invd >= 0, else the hi plane. */
+typedef struct { float A[3], B[3]; int lo_near[3]; } qray;
+static inline qray qray_init(const ora_bvh* bvh, v3 o, const float invd[3]) {
+    qray q;
+    const float oo[3] = {o.x, o.y, o.z};
+    for (int a = 0; a < 3; a++) {
+        q.A[a] = bvh->q_step[a] * invd[a];
+        q.B[a] = fmaf(-8388608.0f, q.A[a], fmaf(bvh->q_lo[a], invd[a], -(oo[a] * invd[a])));
+        q.lo_near[a] = invd[a] >= 0.0f;
+    }
+    return q;
+}
+static inline float qplane(uint32_t idx, float A, float B) {
+    union { uint32_t u; float f; } m;
+    m.u = 0x4B000000u | idx;
+    return fmaf(m.f, A, B);
+}
+static inline int bvh_qslab(const uint32_t w[3], const qray* q, float best_t, float* tn_out) {
+    float n[3], f[3];
+    for (int a = 0; a < 3; a++) {
+        const uint32_t lo = w[a] & 0xffffu, hi = w[a] >> 16;
+        n[a] = qplane(q->lo_near[a] ? lo : hi, q->A[a], q->B[a]);
+        f[a] = qplane(q->lo_near[a] ? hi : lo, q->A[a], q->B[a]);
+    }
+    float tn = fmaxf(fmaxf(n[0], n[1]), fmaxf(n[2], 0.0f));
+    float tf = fminf(fminf(f[0], f[1]), fminf(f[2], best_t));
+    *tn_out = tn;
+    return tn <= tf;
+}
+
 /* BUILD-DEFINED traversal over the 4-wide tree (the specification of node-visit counts):
  *  - `cur` >= 0: fetch the node (visits++), slab-test its four child boxes against [0, best_t].
  *      closest-hit: descend into the NEAREST hit child = smallest key (bits of its entry distance tn with the
@@ -520,6 +553,7 @@ static int bvh_query2(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, 
                      uint32_t* visits, qctr* c) {
     float invd[3] = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
     float ood[3] = {o.x * invd[0], o.y * invd[1], o.z * invd[2]};
+    const qray qr = bvh->qnodes ? qray_init(bvh, o, invd) : (qray){{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     int32_t stack_ref[ORA_STACK];
     float stack_tn[ORA_STACK];
     int sp = 0;
@@ -536,8 +570,15 @@ static int bvh_query2(const ora_triangle* tris, const ora_bvh* bvh, v3 o, v3 d, 
             (*visits)++;
             c->nodes++;
             float tn0, tn1;
-            int h0 = nd->child0 != 0x7fffffff && bvh_slab(nd->c0, nd->e0, invd, ood, best_t, &tn0);
-            int h1 = nd->child1 != 0x7fffffff && bvh_slab(nd->c1, nd->e1, invd, ood, best_t, &tn1);
+            int h0, h1;
+            if (bvh->qnodes) { /* the product walks the quantised encoding of this tree */
+                const uint32_t* w = bvh->qnodes + (size_t)cur * 8;
+                h0 = nd->child0 != 0x7fffffff && bvh_qslab(w, &qr, best_t, &tn0);
+                h1 = nd->child1 != 0x7fffffff && bvh_qslab(w + 3, &qr, best_t, &tn1);
+            } else {
+                h0 = nd->child0 != 0x7fffffff && bvh_slab(nd->c0, nd->e0, invd, ood, best_t, &tn0);
+                h1 = nd->child1 != 0x7fffffff && bvh_slab(nd->c1, nd->e1, invd, ood, best_t, &tn1);
+            }
             if (h0 && h1) {
                 if (tn1 < tn0) {
                     stack_ref[sp] = nd->child0; stack_tn[sp] = tn0; sp++;

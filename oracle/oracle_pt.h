@@ -106,7 +106,16 @@ typedef struct ora_bvh {
     const int32_t* tri_order; /* BVH position -> index into the caller's triangle array */
     int32_t n_tris;
     int32_t width;
+    /* width 2 only: the QUANTISED encoding the product traverses (include/SharedHeader.h: ptb_bvh_nodeq), or NULL = walk the
+     * fp32 boxes.  8 x uint32 per node: per child and axis one word (lo plane | hi plane << 16) on the grid below, then
+     * the two child references. */
+    const uint32_t* qnodes;
+    float q_lo[3], q_step[3];
 } ora_bvh;
+
+/* BUILD-DEFINED quantisation of a binary tree ("Quantised binary nodes"): a pure function of the fp32
+ * node array.  q_out: 8 * n_nodes words. */
+int ora_bvh_quantize(const ora_bvh_node* nodes, int n_nodes, uint32_t* q_out, float q_lo[3], float q_step[3]);
 
 enum { ORA_MODE_PRIMARY = 0, ORA_MODE_AO = 1, ORA_MODE_DIRECT = 2, ORA_MODE_PATH = 3 };
 enum { ORA_ACCUM_REFERENCE = 0, ORA_ACCUM_LINEAR = 1 };

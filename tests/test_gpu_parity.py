@@ -570,6 +570,27 @@ def test_path_regeneration_equals_one_sample_per_thread(dev, pt, scene):
     assert res[0] == res[1]
 
 
+@pytest.mark.parametrize("build", ["host_cornell", "host_tess", "device_lbvh"])
+def test_quantised_nodes_equal_the_oracles(dev, pt, ob, cornell, build):
+    """Binary trees are traversed through their 32-byte quantised encoding (ptb_bvh_nodeq), derived on the device from the fp32
+    nodes for host-built and device-built trees alike: its bytes and grid equal the oracle's restatement (ora_bvh_quantize)
+    applied to the same fp32 nodes."""
+    tris, mats = cornell
+    if build == "host_cornell":
+        sc = dev.scene(tris, mats, pt.bvh_params(force_width=2))
+    elif build == "host_tess":
+        sc = dev.scene(pt.tessellate(tris, 20), mats)
+    else:
+        sc = dev.scene(pt.tessellate(tris, 9), mats, gpu_build=True)
+    assert sc.info()["width"] == 2
+    nodes, _order = sc.bvh()
+    q, lo, step = sc.bvh_quantized()
+    oq, olo, ostep = ob.quantize(nodes)
+    assert lo == olo and step == ostep
+    assert q.tobytes() == oq.tobytes()
+    sc.close()
+
+
 @pytest.mark.parametrize("form", ["flat", "wide4", "binary_smem", "binary_global"])
 def test_path_state_machine_is_scheduling_only(dev, pt, cornell, form):
     """k_path_sm (per-lane state machine, the warp votes which phase runs: tune[5]=3) against k_mega_path_regen (tune[5]=2)

@@ -143,6 +143,52 @@ def test_trace_random_rays_brute_vs_bvh(ob, cornell, width):
                 np.testing.assert_array_equal(bits(a[f]), bits(b[f]))
 
 
+@pytest.mark.parametrize("k", [1, 6])
+def test_quantised_binary_nodes(ob, cornell, k):
+    """ora_bvh_quantize (rules Q1-Q3): every quantised box contains its fp32 box with at least one grid step to spare on each
+    side, empty slots can never be hit, and walking the quantised boxes finds exactly the hits of the brute-force loop (and of
+    the fp32 boxes) -- also for rays that start far outside the scene and for axis-parallel rays."""
+    tris, _ = cornell
+    big = ob.tessellate(tris, k) if k > 1 else tris
+    b = ob.build_bvh(big, width=2)
+    nodes = b["nodes"]
+    q, lo, step = ob.quantize(nodes)
+    assert q.shape == (len(nodes), 8) and all(s > 0 for s in step)
+    for child, (cf, ef, rf) in enumerate((("c0", "e0", "child0"), ("c1", "e1", "child1"))):
+        live = nodes[rf] != 0x7FFFFFFF
+        for a in range(3):
+            w = q[:, 3 * child + a]
+            ql, qh = (w & 0xFFFF).astype(np.float64), (w >> 16).astype(np.float64)
+            plo = nodes[cf][:, a].astype(np.float64) - nodes[ef][:, a].astype(np.float64)
+            phi = nodes[cf][:, a].astype(np.float64) + nodes[ef][:, a].astype(np.float64)
+            assert (lo[a] + ql[live] * step[a] <= plo[live] - 0.999 * step[a]).all()
+            assert (lo[a] + qh[live] * step[a] >= phi[live] + 0.999 * step[a]).all()
+            assert ((ql[live] > 0) & (qh[live] < 65535)).all()  # the grid margin keeps the clamp out of play
+            assert (ql[~live] == 65535).all() and (qh[~live] == 0).all()
+    assert (q[:, 6].view(np.int32) == nodes["child0"]).all() and (q[:, 7].view(np.int32) == nodes["child1"]).all()
+    bq, _k1 = ob.make_bvh(nodes, b["tri_order"])
+    bf, _k2 = ob.make_bvh(nodes, b["tri_order"], quantized=False)
+    rng = np.random.default_rng(11)
+    n = 60_000
+    o = rng.uniform([-2.7, 0.05, -5.5], [2.7, 5.4, 3.0], (n, 3)).astype(np.float32)
+    o[:5000] *= np.float32(7.0)  # far outside the grid
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d[5000:5100] = np.float32([0, 0, -1]); d[5100:5200] = np.float32([0, -1, 0]); d[5200:5300] = np.float32([1, 0, 0])
+    for any_hit, tmax in ((False, 1e20), (True, 2.0)):
+        brute = ob.trace(big, o, d, tmax, bvh=None, any_hit=any_hit)
+        for tree in (bq, bf):
+            got = ob.trace(big, o, d, tmax, bvh=tree, any_hit=any_hit)
+            np.testing.assert_array_equal(brute["tri"] >= 0, got["tri"] >= 0)
+            if not any_hit:
+                for f in ("tri", "t", "u", "v"):
+                    np.testing.assert_array_equal(bits(brute[f]), bits(got[f]))
+    # the quantised boxes are a little larger: never fewer node visits than the fp32 boxes
+    vq = ob.trace(big, o, d, 1e20, bvh=bq)["visits"].astype(np.int64)
+    vf = ob.trace(big, o, d, 1e20, bvh=bf)["visits"].astype(np.int64)
+    assert (vq >= vf).all() and vq.sum() < 1.1 * vf.sum()
+
+
 def test_reference_accumulation_semantics(ob, cornell):
     """GenerateColors.cl:314-321: gamma-space running mean whose weights drop frame 0."""
     tris, mats = cornell
