@@ -497,7 +497,7 @@ template <bool STATS>
 PTD_FI bool node_step2_bf(const Ctx& c, const RayPre& rp, float best_t, int& cur, int& sp, QueryStats& qs) {
     uint4 a, b;
     ldg_nodeq(c.g_nodes, cur, a, b);
-    const uint2 top = c.lstack[sp > 0 ? sp - 1 : 0];
+    const uint2 top = c.lstack[sp - 1];  // sp = 0 reads the spare slot below the stack (value unused): no clamp, the -1 folds into the address
     if (STATS) qs.visits++;
     float tn0, tn1;
     const bool h0 = qslab(a.x, a.y, a.z, rp, best_t, tn0);
@@ -528,8 +528,8 @@ template <int SMALL, bool STATS, int MINB, int NSTEP = 1>
 __global__ void __launch_bounds__(128, MINB) k_path_sm(const SceneDev sc, const RenderArgs a, unsigned long long* work_counter) {
     extern __shared__ __align__(16) unsigned char smem[];
     Ctx c = stage_scene<true, SMALL>(sc, smem);
-    uint2 lstack_mem[PTD_LSTACK_ENTRIES];
-    if (!SMALL && sc.lstack) c.lstack = lstack_mem;
+    uint2 lstack_mem[PTD_LSTACK_ENTRIES + 1];  // [0] = spare slot below the stack (node_step2_bf reads the top speculatively)
+    if (!SMALL && sc.lstack) c.lstack = lstack_mem + 1;
     const bool fast_nodes = SMALL == PTD_LARGE && sc.lstack && sc.smem_nodes == 0;  // warp-uniform: node_step2_bf applies
     const long long total = (long long)a.frames_in_batch * a.n_local;
     const unsigned lane = threadIdx.x & 31u;

@@ -327,8 +327,8 @@ __global__ void __launch_bounds__(128) wf_extend_p(const SceneDev sc, const WfBu
     if (blockIdx.x * blockDim.x >= n) return;
     extern __shared__ __align__(16) unsigned char smem[];
     Ctx c = stage_scene<true, SMALL>(sc, smem);
-    uint2 lstack_mem[PTD_LSTACK_ENTRIES];
-    if (!SMALL && sc.lstack) c.lstack = lstack_mem;
+    uint2 lstack_mem[PTD_LSTACK_ENTRIES + 1];  // [0] = spare slot below the stack (node_step2_bf reads the top speculatively)
+    if (!SMALL && sc.lstack) c.lstack = lstack_mem + 1;
     ExtendStore<SMALL, STATS> io;
     io.qo = w.q_o[qi]; io.qd = w.q_d[qi]; io.hit = w.hit; io.slot_stats = w.slot_stats; io.depth = depth; io.slot = 0;
     io.c = &c;
