@@ -9,8 +9,9 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "oclpathtracer_b200", "libptb200.so")
 HOT = [  # (mangled fragment, what)
-    ("k_mega_path_regenILb1ELi0ELb0", "k_mega_path_regen<BVH, LARGE>   C5: 2M-triangle scene, binary tree from L2/HBM"),
-    ("k_mega_path_regenILb1ELi2ELb0", "k_mega_path_regen<BVH, FLAT>    C4: Cornell box, flat leaf boxes"),
+    ("k_path_smILi0ELb0ELi8ELi6", "k_path_sm<LARGE, 8 CTAs/SM, 6 visits per vote>   C5: 2M-triangle scene, quantised binary nodes from L2/HBM"),
+    ("k_mega_path_regenILb1ELi0ELb0ELb0", "k_mega_path_regen<BVH, LARGE>   the while-while form of the same (tune[5] = 2)"),
+    ("k_mega_path_regenILb1ELi2ELb0ELb1", "k_mega_path_regen<BVH, FLAT, COOP>    C4: Cornell box, flat leaf boxes, pooled triangle phase"),
     ("k_megaILi1ELb1ELi2ELb0", "k_mega<AO, BVH, FLAT>           C2"),
     ("k_megaILi2ELb1ELi1ELb0", "k_mega<DIRECT, BVH, SMALL4>     C3: Cornell box, 4-wide tree"),
     ("k_megaILi0ELb1ELi2ELb0", "k_mega<PRIMARY, BVH, FLAT>      C1"),
