@@ -82,7 +82,7 @@ def config_of(name, world):
             "step": f"one full pass over the configuration: {wl['spp']} sample(s) per pixel of ONE {wl['width']}x{wl['height']} image",
             "scene_triangles": 36 * (wl.get("tess", 1) ** 2),
             "parallelism": f"image tile-sharded over {world} GPU(s) (64-pixel blocks round-robin), one image per step",
-            "l2": "a 256 MiB flush runs between timed steps (and the 2M-triangle scene, 162 MB of nodes + triangles, exceeds the 126 MB L2)"}
+            "l2": "a 256 MiB flush runs between timed steps (and the 2M-triangle scene, 33 MB of quantised nodes + 96 MB of triangles, exceeds the 126 MB L2)"}
 
 
 def bind_to_gpu_numa(gpu_index):
