@@ -740,6 +740,28 @@ static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::Re
                     if (a.tune[14] == 2) k = ptd::k_path_sm<SMALL, STATS, 8, 2>;
                     if (a.tune[14] == 4) k = ptd::k_path_sm<SMALL, STATS, 8, 4>;
                 }
+                // Large scenes on the local-memory stack: the form with the path state parked in shared memory (k_path_sm2), 10 CTAs per SM
+                // (48 registers) without statistics.  tune[12] = 1: the registers-only k_path_sm; 28 / 29 / 31: 8 / 9 / 11 CTAs; 32 / 33: 4 / 8
+                // visits per vote (A/B runs).
+                if constexpr (SMALL == ptd::PTD_LARGE) {
+                    if (a.tune[12] != 1 && a.tune[12] != 9 && a.tune[14] == 0 && sc2.lstack && sc2.smem_nodes == 0 && total < (1ll << 31) && a.tune[9] <= 0) {
+                        auto k2 = ptd::k_path_sm2<STATS, STATS ? 0 : 10, 6>;
+                        if constexpr (!STATS) {
+                            if (a.tune[12] == 28) k2 = ptd::k_path_sm2<false, 8, 6>;
+                            if (a.tune[12] == 29) k2 = ptd::k_path_sm2<false, 9, 6>;
+                            if (a.tune[12] == 31) k2 = ptd::k_path_sm2<false, 11, 6>;
+                            if (a.tune[12] == 32) k2 = ptd::k_path_sm2<false, 10, 4>;
+                            if (a.tune[12] == 33) k2 = ptd::k_path_sm2<false, 10, 8>;
+                        }
+                        const size_t sm2 = ptd::path_sm2_smem_bytes(block);
+                        if (int rc = set_smem(k2, sm2, block, &per_sm)) return rc;
+                        long long grid2 = (long long)per_sm * dev->prop.multiProcessorCount;
+                        if (grid2 > need) grid2 = need;
+                        k2<<<(unsigned)grid2, block, sm2, dev->stream>>>(sc2, a, work);
+                        CU_TRY(cudaGetLastError());
+                        return PTB_OK;
+                    }
+                }
                 if (int rc = set_smem(k, smem2, block, &per_sm)) return rc;
                 if (a.tune[9] < 0 && -a.tune[9] < per_sm) per_sm = -a.tune[9];  // tune[9] = -n: n resident CTAs per SM (latency-sensitivity measurements)
                 long long grid = (long long)per_sm * dev->prop.multiProcessorCount;

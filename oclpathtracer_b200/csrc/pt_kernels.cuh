@@ -675,6 +675,162 @@ __global__ void __launch_bounds__(128, MINB) k_path_sm(const SceneDev sc, const 
     }
 }
 
+// ---- k_path_sm with the path state parked in shared memory ------------------------------------------------------------
+// The walk loop of k_path_sm needs the box-test constants, best_t, the current reference and the stack height; everything
+// else a lane carries (ray, hit record, radiance, mask, seed, slot, depth: 19 words) is only touched by the triangle test,
+// the shade phase and the regeneration.  Here those words live in a per-thread shared-memory column (conflict-free: word f of
+// thread t at f * 512 + t * 4), loaded where a phase needs them, so the walk loop fits a lower register cap and more CTAs are
+// resident per SM (the kernel hides dependent-load latency with resident warps: 8 -> 7 CTAs cost 7.5 %).  Large scenes with the
+// local-memory stack and no staged prefix only; per-sample arithmetic and order unchanged.  Measured on C5 (same kernel body,
+// 6 visits per vote): registers only, 8 CTAs 4.36 Grays/s; parked, 8 / 9 / 10 / 11 CTAs (64 / 56 / 48 / 40 registers): 4.43 / 4.58 /
+// 4.61 / 4.62 with the old quorums, 4.69 at 10 CTAs with the re-tuned ones.
+enum { PK_OX = 0, PK_OY, PK_OZ, PK_DX, PK_DY, PK_DZ, PK_U, PK_V, PK_POS, PK_IDX, PK_RX, PK_RY, PK_RZ, PK_MX, PK_MY, PK_MZ, PK_SEED, PK_SLOT, PK_DEPTH, PK_FIELDS };
+static inline size_t path_sm2_smem_bytes(int block) { return 16 + (size_t)PK_FIELDS * block * 4; }
+
+template <bool STATS, int MINB, int NSTEP>
+__global__ void __launch_bounds__(128, MINB) k_path_sm2(const SceneDev sc, const RenderArgs a, unsigned long long* work_counter) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Ctx c = stage_scene<true, PTD_LARGE>(sc, smem);  // stages nothing (smem_nodes == 0): only the Ctx
+    uint2 lstack_mem[PTD_LSTACK_ENTRIES + 1];
+    c.lstack = lstack_mem + 1;
+    const uint32_t pk = smem_u32(smem) + 16u + threadIdx.x * 4u;
+    const uint32_t fstride = blockDim.x * 4u;
+#define PKL(f) lds32(pk + (uint32_t)(f) * fstride)
+#define PKLF(f) __uint_as_float(lds32(pk + (uint32_t)(f) * fstride))
+#define PKS(f, v) sts32(pk + (uint32_t)(f) * fstride, (uint32_t)(v))
+#define PKSF(f, v) sts32(pk + (uint32_t)(f) * fstride, __float_as_uint(v))
+    const uint32_t total = (uint32_t)((long long)a.frames_in_batch * a.n_local);  // the launcher guarantees < 2^31 slots
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t thr_regen = a.tune[0] > 0 ? a.tune[0] : 4;   // quorums re-tuned for 10 resident CTAs (sweep: shade 16 / 20 / 24 -> 4.61 / 4.66 / 4.51,
+    const uint32_t thr_shade = a.tune[10] > 0 ? a.tune[10] : 20;  //  regen 4 / 6 / 8 -> 4.69 / 4.66 / 4.59 Grays/s)
+    const uint32_t thr_leaf = a.tune[11] > 0 ? a.tune[11] : 10;
+    RayCount rc{0u, 0u};
+    QueryStats qs{0u, 0u};
+    uint32_t state = ST_REGEN;
+    bool exhausted = false;
+    int li = 0, frame = 0;  // STATS only
+    uint32_t tests0 = 0, visits0 = 0;
+    RayPre rp{mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 0.f), {0u, 0u, 0u}};
+    float best_t = 1e20f;
+    int cur = 0, sp = 0;
+    SampleStats<STATS> st{};
+    auto begin_query = [&](const Ray& r) {
+        visits0 = qs.visits;
+        best_t = 1e20f;
+        PKS(PK_IDX, -1);
+        rp = ray_pre<PTD_LARGE>(c, r.o, r.d);
+        cur = 0; sp = 0;
+        state = ST_NODE;
+    };
+    for (;;) {
+        for (;;) {
+            const uint32_t cnt = __reduce_add_sync(0xffffffffu, state);
+            const uint32_t n_node = (cnt >> 8) & 255u, n_leaf = (cnt >> 16) & 255u, n_shade = cnt >> 24;
+            if (n_leaf >= thr_leaf || (n_leaf && !n_node)) {
+                if (state == ST_LEAF) {
+                    const int k = (int)((uint32_t)(~cur) >> 3);
+                    V3 p1, e1, e2; int idx, quad;
+                    load_tri<PTD_LARGE>(c, k, p1, e1, e2, idx, quad);
+                    const V3 o = mk(PKLF(PK_OX), PKLF(PK_OY), PKLF(PK_OZ)), d = mk(PKLF(PK_DX), PKLF(PK_DY), PKLF(PK_DZ));
+                    float t, u, v;
+                    if (STATS) qs.tests++;
+                    if (mt_core(o, d, p1, e1, e2, t, u, v)) {
+                        bool take = t < best_t;
+                        if (t == best_t) { const int bi = (int)PKL(PK_IDX); take = bi >= 0 && idx < bi; }
+                        if (take) {
+                            best_t = t;
+                            PKSF(PK_U, u); PKSF(PK_V, v); PKS(PK_POS, k); PKS(PK_IDX, idx);
+                        }
+                    }
+                    const uint32_t code = (uint32_t)(~cur);
+                    if (code & 7u) cur = (int)~(((code >> 3) + 1u) << 3 | ((code & 7u) - 1u));
+                    else if (stack_pop<false>(c, sp, cur, best_t)) state = cur >= 0 ? ST_NODE : ST_LEAF;
+                    else state = ST_SHADE;
+                }
+                continue;
+            }
+            if (!n_node || n_shade >= thr_shade) break;
+            if (state == ST_NODE) {
+                bool more = node_step2_bf<STATS>(c, rp, best_t, cur, sp, qs);
+#pragma unroll
+                for (int rep = 1; rep < NSTEP; ++rep)
+                    if (more && cur >= 0) more = node_step2_bf<STATS>(c, rp, best_t, cur, sp, qs);
+                state = !more ? ST_SHADE : cur >= 0 ? ST_NODE : ST_LEAF;
+            }
+        }
+        if (state == ST_SHADE) {
+            Ray r{mk(PKLF(PK_OX), PKLF(PK_OY), PKLF(PK_OZ)), mk(PKLF(PK_DX), PKLF(PK_DY), PKLF(PK_DZ))};
+            V3 radiance = mk(PKLF(PK_RX), PKLF(PK_RY), PKLF(PK_RZ)), mask = mk(PKLF(PK_MX), PKLF(PK_MY), PKLF(PK_MZ));
+            uint32_t seed = PKL(PK_SEED);
+            int depth = (int)PKL(PK_DEPTH);
+            Hit h;
+            h.idx = (int)PKL(PK_IDX);
+            const bool hit = h.idx >= 0;
+            h.t = best_t; h.u = PKLF(PK_U); h.v = PKLF(PK_V); h.pos = (int)PKL(PK_POS);
+            rc.closest++;
+            const bool more = path_after_hit<PTD_LARGE, STATS>(c, hit, h, r, seed, radiance, mask, depth, a.max_depth, st, qs.visits - visits0);
+            ++depth;
+            if (!more || depth >= a.max_depth) {
+                a.samples[PKL(PK_SLOT)] = make_float4(cl_max(radiance.x, 0.0f), cl_max(radiance.y, 0.0f), cl_max(radiance.z, 0.0f), 1.0f);  // :260
+                if constexpr (STATS) {
+                    if (a.stats && frame == a.stats_frame) {
+                        uint4* dst = reinterpret_cast<uint4*>(a.stats + li);
+                        dst[0] = make_uint4((uint32_t)st.tri, (uint32_t)st.quad, st.t_bits, st.visits_primary);
+                        dst[1] = make_uint4(st.visits_secondary, st.count, st.id_hash, qs.tests - tests0);
+                    }
+                }
+                state = exhausted ? ST_DONE : ST_REGEN;
+            } else {
+                PKSF(PK_OX, r.o.x); PKSF(PK_OY, r.o.y); PKSF(PK_OZ, r.o.z); PKSF(PK_DX, r.d.x); PKSF(PK_DY, r.d.y); PKSF(PK_DZ, r.d.z);
+                PKSF(PK_RX, radiance.x); PKSF(PK_RY, radiance.y); PKSF(PK_RZ, radiance.z);
+                PKSF(PK_MX, mask.x); PKSF(PK_MY, mask.y); PKSF(PK_MZ, mask.z);
+                PKS(PK_SEED, seed); PKS(PK_DEPTH, depth);
+                begin_query(r);
+            }
+        }
+        const unsigned m_regen = __ballot_sync(0xffffffffu, state == ST_REGEN);
+        const unsigned m_walk = __ballot_sync(0xffffffffu, (state & (ST_NODE | ST_LEAF)) != 0u);
+        const uint32_t n_regen = __popc(m_regen);
+        if (n_regen && (n_regen >= thr_regen || !m_walk)) {
+            const int leader = __ffs(m_regen) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)n_regen);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + n_regen >= (unsigned long long)total) exhausted = true;
+            if (state == ST_REGEN) {
+                const unsigned long long slot = base + __popc(m_regen & ((1u << lane) - 1u));
+                if (slot >= (unsigned long long)total) {
+                    state = ST_DONE;
+                } else {
+                    const int fi = (int)(slot / (unsigned)a.n_local);
+                    const int l = (int)(slot - (unsigned long long)fi * (unsigned)a.n_local);
+                    const int gid = gid_of_local(a.shard, l);
+                    li = l; frame = a.first_frame + fi;
+                    uint32_t seed = (uint32_t)gid + hash_uint32((uint32_t)(a.first_frame + fi));  // GenerateColors.cl:308
+                    const Ray r = generate_ray(gid % a.width, gid / a.width, CamScale{a.cam_inv_w, a.cam_inv_h, a.cam_aspect}, seed);  // :310
+                    PKSF(PK_OX, r.o.x); PKSF(PK_OY, r.o.y); PKSF(PK_OZ, r.o.z); PKSF(PK_DX, r.d.x); PKSF(PK_DY, r.d.y); PKSF(PK_DZ, r.d.z);
+                    PKSF(PK_RX, 0.0f); PKSF(PK_RY, 0.0f); PKSF(PK_RZ, 0.0f); PKSF(PK_MX, 1.0f); PKSF(PK_MY, 1.0f); PKSF(PK_MZ, 1.0f);
+                    PKS(PK_SEED, seed); PKS(PK_SLOT, (uint32_t)slot); PKS(PK_DEPTH, 0);
+                    st = SampleStats<STATS>{};
+                    tests0 = qs.tests;
+                    begin_query(r);
+                }
+            }
+        } else if (!m_walk) {
+            break;
+        }
+    }
+#undef PKL
+#undef PKLF
+#undef PKS
+#undef PKSF
+    flush_counter(a.counters, CTR_CLOSEST, rc.closest);
+    if (STATS) {
+        flush_counter(a.counters, CTR_NODES, qs.visits);
+        flush_counter(a.counters, CTR_TESTS, qs.tests);
+    }
+}
+
 // ---- ordered accumulation of a batch: GenerateColors.cl:290-321 --------------------------------
 
 PTD_FI V3 gamma_correct(V3 v) {  // :290-294

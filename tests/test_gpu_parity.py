@@ -607,18 +607,21 @@ def test_path_state_machine_is_scheduling_only(dev, pt, cornell, form):
               integrator=pt.INTEGRATOR_MEGAKERNEL, frames_per_batch=2)
     res = []
     try:
-        for variant, thr in ((1, (0, 0, 0)), (2, (0, 0, 0)), (3, (0, 0, 0)), (3, (1, 1, 1)), (3, (32, 32, 32)), (3, (3, 20, 2)), (3, (12, 2, 27))):
+        # tune[12]: 0 = k_path_sm2 (path state parked in shared memory; large scenes on the local-memory stack), 1 = k_path_sm, 28 = sm2 at 8 CTAs
+        for variant, thr, t12 in ((1, (0, 0, 0), 0), (2, (0, 0, 0), 0), (3, (0, 0, 0), 0), (3, (1, 1, 1), 0), (3, (32, 32, 32), 0), (3, (3, 20, 2), 0),
+                                  (3, (12, 2, 27), 0), (3, (0, 0, 0), 1), (3, (2, 31, 3), 1), (3, (0, 0, 0), 28), (0, (0, 0, 0), 0), (0, (1, 1, 1), 0)):
             dev.set_tuning(5, variant)
+            dev.set_tuning(12, t12)
             for k, v in zip((0, 10, 11), thr):
                 dev.set_tuning(k, v)
             for stats_on in (1, 0):
                 frame, stats = dev.buffer(w * h * 16), dev.buffer(w * h * 32)
                 ctr = dev.render(sc, pt.default_params(**{**kw, "collect_stats": stats_on}), frame, stats if stats_on else None, want_counters=True)
-                res.append((variant, thr, stats_on, frame.read(np.uint32).tobytes(), stats.read(np.uint32).tobytes() if stats_on else b"",
+                res.append(((variant, t12), thr, stats_on, frame.read(np.uint32).tobytes(), stats.read(np.uint32).tobytes() if stats_on else b"",
                             (ctr["rays_closest"], ctr["samples"]) + ((ctr["nodes"], ctr["tri_tests"]) if stats_on else ())))
                 frame.close(); stats.close()
     finally:
-        for k in (5, 0, 10, 11):
+        for k in (5, 0, 10, 11, 12):
             dev.set_tuning(k, 0)
         sc.close()
     for r in res:
