@@ -543,7 +543,7 @@ def main():
     integ_ms = prof["integrator_ms"] / max(1, prof["batches"])          # mean duration of one integrator launch (CUDA events, live)
     rays_per_launch = rays_all / world / max(1, prof["batches"])
     tr = ncu_traffic(args.workload)
-    roof = {"kernel": ("k_path_sm" if wl.get("tess") else "k_mega_path_regen") if wl["mode"] == 3 else "k_mega", "kernel_ms": integ_ms,
+    roof = {"kernel": ("k_path_sm2" if wl.get("tess") else "k_mega_path_regen") if wl["mode"] == 3 else "k_mega", "kernel_ms": integ_ms,
             "launches_per_step": prof["batches"] / max(1, args.steps),
             "kernel_share_of_step": (prof["integrator_ms"] / max(1e-9, sum(ms_steps))) if world == 1 else None,
             "rays_per_launch": rays_per_launch, "peak_source": peak_src}
@@ -575,8 +575,8 @@ def main():
                      "l2": {"algorithmic_bytes_per_ray": alg, "achieved": alg * rate / 1e9, "peak": l2_peak, "unit": "GB/s", "frac": alg * rate / 1e9 / l2_peak,
                             "note": "SURVEY 8d's algorithmic bytes (nodes*32 [quantised 32-byte records] + tri_tests*48 + 16 B/sample) are the L1/L2 stream, quoted against the L2 bandwidth cap"},
                      "simt": simt,
-                     "binding": "issue slots (ncu: 65 % busy at 15.2 of 32 lanes) together with long-scoreboard stalls on dependent node fetches (5.0 per issue, "
-                                "8 CTAs of 4 warps per SM); the L1 data pipe runs at 50 % (84 % before the nodes were quantised), L2 at 24 %, HBM at 4 %",
+                     "binding": "issue slots (ncu: 71 % busy at 15.7 of 32 lanes) together with long-scoreboard stalls on dependent node fetches (5.7 per issue, "
+                                "10 CTAs of 4 warps per SM); the L1 data pipe runs at 64 % (84 % before the nodes were quantised), L2 at 30 %, HBM at 5 %",
                      "note": "achieved = warp instructions per ray of the committed ncu capture (profiles/ncu_traffic.json) x rays per second measured live with CUDA "
                              "events; traffic = dram__bytes_read + dram__bytes_write per launch of the same capture scaled to this launch's rays"})
     elif rank == 0:
