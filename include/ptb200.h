@@ -262,11 +262,22 @@ int ptb_device_profile(ptb_device* dev, int enable);
  * synchronises, returns the totals since the previous read and clears them) -- exact ray counts over a whole timed
  * region without a synchronisation inside it.  cumulative = 0 restores the default; -1 leaves the mode as it is.      */
 int ptb_device_counters(ptb_device* dev, int cumulative, ptb_counters* out);
-/* experiment knobs for A/B measurements (results never change).  index: 1 = log2 multiplier of
- * the frame-ahead batch of ptb_launch1d; 2 = 2: keep the traversal stack of large scenes in shared memory; 3 = CTA
- * size 64 | 32 (default 128); 4 = BVH nodes staged per CTA for large scenes (default 64); 5 = 1: one sample per
- * thread instead of path regeneration; 6 = 1: wavefront stages without persistent ray fetch; 7 = idle-lane count
- * that triggers a refill (default 8); 0 = waiting lanes that trigger path regeneration (default 6).                                                                  */
+/* experiment knobs for A/B measurements (results never change); 0 = the default everywhere.  index:
+ *  0  waiting lanes that trigger path regeneration (default 6; 4 in the large-scene state-machine kernel)
+ *  1  log2 multiplier of the frame-ahead batch of ptb_launch1d
+ *  2  = 2: keep the traversal stack of large scenes in shared memory instead of local memory
+ *  3  CTA size 64 | 32 (default 128) of the megakernels
+ *  4  BVH nodes staged per CTA for large scenes (default 0: none)
+ *  5  PATH kernel: 1 = one sample per thread, 2 = while-while query inside a persistent path segment (k_mega_path_regen),
+ *     3 = per-lane state machine (k_path_sm) for every scene form; default: state machine for large scenes, 2 otherwise
+ *  6  = 1: wavefront stages without persistent ray fetch;  7  idle-lane count that triggers a wavefront refill (default 8)
+ *  9  > 0: extra KB of shared memory per CTA, < 0: -n resident CTAs per SM (occupancy / latency sensitivity runs)
+ *  10 lanes waiting for the shade phase, 11 lanes at a leaf, that make the state-machine kernels switch phase (defaults 20 | 16, 10)
+ *  12 large-scene PATH kernel: 1 = registers-only k_path_sm (8 CTAs per SM), 9 = the same at 9 CTAs; default k_path_sm2 (path state
+ *     parked in shared memory, 10 CTAs), 28 | 29 | 31 = at 8 | 9 | 11 CTAs, 32 | 33 = 4 | 8 node visits per vote (default 6)
+ *  13 = 1: wavefront extend in the while-while form for large scenes; = 2: FLAT scenes without the pooled triangle phase
+ *  14 registers-only k_path_sm: 1 | 2 | 4 node visits per vote
+ *  15 log2 of the sample slots kept in flight per launch (default 2^27 for PATH, 2^22 otherwise)                              */
 int ptb_device_set_tuning(ptb_device* dev, int index, int value);
 int ptb_device_profile_read(ptb_device* dev, float* integrator_ms, float* resolve_ms, int* integrator_launches,
                             uint64_t* kernel_launches);
