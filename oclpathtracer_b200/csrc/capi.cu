@@ -744,7 +744,7 @@ static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::Re
                 // (48 registers) without statistics.  tune[12] = 1: the registers-only k_path_sm; 28 / 29 / 31: 8 / 9 / 11 CTAs; 32 / 33: 4 / 8
                 // visits per vote (A/B runs).
                 if constexpr (SMALL == ptd::PTD_LARGE) {
-                    if (a.tune[12] != 1 && a.tune[12] != 9 && a.tune[14] == 0 && sc2.lstack && sc2.smem_nodes == 0 && total < (1ll << 31) && a.tune[9] <= 0) {
+                    if (a.tune[12] != 1 && a.tune[12] != 9 && a.tune[14] == 0 && sc2.lstack && sc2.smem_nodes == 0 && total < (1ll << 31) && a.tune[9] <= 0 && block == 128) {
                         auto k2 = ptd::k_path_sm2<STATS, STATS ? 0 : 10, 6>;
                         if constexpr (!STATS) {
                             if (a.tune[12] == 28) k2 = ptd::k_path_sm2<false, 8, 6>;

@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(128, MINB) k_path_sm2(const SceneDev sc, const
     uint2 lstack_mem[PTD_LSTACK_ENTRIES + 1];
     c.lstack = lstack_mem + 1;
     const uint32_t pk = smem_u32(smem) + 16u + threadIdx.x * 4u;
-    const uint32_t fstride = blockDim.x * 4u;
+    constexpr uint32_t fstride = 128u * 4u;  // the launcher runs this kernel with 128-thread CTAs only: field offsets are immediates
 #define PKL(f) lds32(pk + (uint32_t)(f) * fstride)
 #define PKLF(f) __uint_as_float(lds32(pk + (uint32_t)(f) * fstride))
 #define PKS(f, v) sts32(pk + (uint32_t)(f) * fstride, (uint32_t)(v))
