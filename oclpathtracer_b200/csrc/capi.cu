@@ -753,11 +753,15 @@ static int launch_mega_t(ptb_device* dev, const ptd::SceneDev& sc, const ptd::Re
                             if (a.tune[12] == 32) k2 = ptd::k_path_sm2<false, 10, 4>;
                             if (a.tune[12] == 33) k2 = ptd::k_path_sm2<false, 10, 8>;
                         }
+                        ptd::RenderArgs a2 = a;  // the kernel reads its quorums as plain parameters
+                        if (a2.tune[0] <= 0) a2.tune[0] = 4;
+                        if (a2.tune[10] <= 0) a2.tune[10] = 20;
+                        if (a2.tune[11] <= 0) a2.tune[11] = 10;
                         const size_t sm2 = ptd::path_sm2_smem_bytes(block);
                         if (int rc = set_smem(k2, sm2, block, &per_sm)) return rc;
                         long long grid2 = (long long)per_sm * dev->prop.multiProcessorCount;
                         if (grid2 > need) grid2 = need;
-                        k2<<<(unsigned)grid2, block, sm2, dev->stream>>>(sc2, a, work);
+                        k2<<<(unsigned)grid2, block, sm2, dev->stream>>>(sc2, a2, work);
                         CU_TRY(cudaGetLastError());
                         return PTB_OK;
                     }

@@ -701,9 +701,9 @@ __global__ void __launch_bounds__(128, MINB) k_path_sm2(const SceneDev sc, const
 #define PKSF(f, v) sts32(pk + (uint32_t)(f) * fstride, __float_as_uint(v))
     const uint32_t total = (uint32_t)((long long)a.frames_in_batch * a.n_local);  // the launcher guarantees < 2^31 slots
     const unsigned lane = threadIdx.x & 31u;
-    const uint32_t thr_regen = a.tune[0] > 0 ? a.tune[0] : 4;   // quorums re-tuned for 10 resident CTAs (sweep: shade 16 / 20 / 24 -> 4.61 / 4.66 / 4.51,
-    const uint32_t thr_shade = a.tune[10] > 0 ? a.tune[10] : 20;  //  regen 4 / 6 / 8 -> 4.69 / 4.66 / 4.59 Grays/s)
-    const uint32_t thr_leaf = a.tune[11] > 0 ? a.tune[11] : 10;
+    // quorums, resolved by the launcher (defaults re-tuned for 10 resident CTAs: shade 16 / 20 / 24 -> 4.61 / 4.66 / 4.51,
+    // regen 4 / 6 / 8 -> 4.69 / 4.66 / 4.59 Grays/s): plain kernel parameters, no select in the loop
+    const uint32_t thr_regen = (uint32_t)a.tune[0], thr_shade = (uint32_t)a.tune[10], thr_leaf = (uint32_t)a.tune[11];
     RayCount rc{0u, 0u};
     QueryStats qs{0u, 0u};
     uint32_t state = ST_REGEN;
