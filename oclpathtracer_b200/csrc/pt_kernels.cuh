@@ -693,7 +693,8 @@ __global__ void __launch_bounds__(128, MINB) k_path_sm2(const SceneDev sc, const
     Ctx c = stage_scene<true, PTD_LARGE>(sc, smem);  // stages nothing (smem_nodes == 0): only the Ctx
     uint2 lstack_mem[PTD_LSTACK_ENTRIES + 1];
     c.lstack = lstack_mem + 1;
-    const uint32_t pk = smem_u32(smem) + 16u + threadIdx.x * 4u;
+    uint32_t pk = smem_u32(smem) + 16u + threadIdx.x * 4u;
+    asm volatile("" : "+r"(pk));  // opaque: kept in a register instead of being re-derived (S2R + shared-window base + LEA, 7 instructions) at every vote
     constexpr uint32_t fstride = 128u * 4u;  // the launcher runs this kernel with 128-thread CTAs only: field offsets are immediates
 #define PKL(f) lds32(pk + (uint32_t)(f) * fstride)
 #define PKLF(f) __uint_as_float(lds32(pk + (uint32_t)(f) * fstride))
