@@ -575,8 +575,8 @@ def main():
                      "l2": {"algorithmic_bytes_per_ray": alg, "achieved": alg * rate / 1e9, "peak": l2_peak, "unit": "GB/s", "frac": alg * rate / 1e9 / l2_peak,
                             "note": "SURVEY 8d's algorithmic bytes (nodes*32 [quantised 32-byte records] + tri_tests*48 + 16 B/sample) are the L1/L2 stream, quoted against the L2 bandwidth cap"},
                      "simt": simt,
-                     "binding": "issue slots (ncu: 68 % busy at 15.3 of 32 lanes) together with long-scoreboard stalls on dependent node fetches (5.8 per issue, "
-                                "9 CTAs of 4 warps per SM); the L1 data pipe runs at 64 % (84 % before the nodes were quantised), L2 at 26 %, HBM at 4 %",
+                     "binding": "issue slots (ncu: 73 % busy at 15.2 of 32 lanes) and the L1 data pipe (74 %) together with long-scoreboard stalls on dependent "
+                                "node fetches (7.5 per issue, 12 CTAs of 4 warps per SM); L2 at 40 %, HBM at 9 %",
                      "note": "achieved = warp instructions per ray of the committed ncu capture (profiles/ncu_traffic.json) x rays per second measured live with CUDA "
                              "events; traffic = dram__bytes_read + dram__bytes_write per launch of the same capture scaled to this launch's rays"})
     elif rank == 0:

@@ -607,9 +607,9 @@ def test_path_state_machine_is_scheduling_only(dev, pt, cornell, form):
               integrator=pt.INTEGRATOR_MEGAKERNEL, frames_per_batch=2)
     res = []
     try:
-        # tune[12]: 0 = k_path_sm2 (path state parked in shared memory; large scenes on the local-memory stack), 1 = k_path_sm, 28 / 30 = sm2 at 8 / 10 CTAs
+        # tune[12]: 0 = k_path_sm2 (path state parked in shared memory; large scenes on the local-memory stack), 1 = k_path_sm, 28 / 29 / 30 = sm2 at 8 / 9 / 10 CTAs (default 11)
         for variant, thr, t12 in ((1, (0, 0, 0), 0), (2, (0, 0, 0), 0), (3, (0, 0, 0), 0), (3, (1, 1, 1), 0), (3, (32, 32, 32), 0), (3, (3, 20, 2), 0),
-                                  (3, (12, 2, 27), 0), (3, (0, 0, 0), 1), (3, (2, 31, 3), 1), (3, (0, 0, 0), 28), (3, (0, 0, 0), 30), (0, (0, 0, 0), 0), (0, (1, 1, 1), 0)):
+                                  (3, (12, 2, 27), 0), (3, (0, 0, 0), 1), (3, (2, 31, 3), 1), (3, (0, 0, 0), 28), (3, (0, 0, 0), 29), (3, (0, 0, 0), 30), (0, (0, 0, 0), 0), (0, (1, 1, 1), 0)):
             dev.set_tuning(5, variant)
             dev.set_tuning(12, t12)
             for k, v in zip((0, 10, 11), thr):

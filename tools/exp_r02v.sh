@@ -1,5 +1,4 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "state_machine or tessellated or c5_two" > gpurun_out/gputest_v.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/gputest_v.log
-SWEEP_REPS=3 timeout 900 python tools/sweep_tune.py c5 32 "" "12=30" "12=31" 2>&1 | tee gpurun_out/sweep_c5_v.txt
+SWEEP_REPS=3 timeout 900 python tools/sweep_tune.py c5 32 "12=31" "12=34" "12=31,10=24" "12=31,10=16" "12=31,11=12" "12=31,11=8" "12=31,0=6" 2>&1 | tee gpurun_out/sweep_c5_v.txt

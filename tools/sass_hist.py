@@ -9,7 +9,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "oclpathtracer_b200", "libptb200.so")
 HOT = [  # (mangled fragment, what)
-    ("k_path_sm2ILb0ELi9ELi6", "k_path_sm2<9 CTAs/SM, 6 visits per vote>   C5: 2M-triangle scene, quantised binary nodes from L2/HBM, path state parked in shared memory"),
+    ("k_path_sm2ILb0ELi11ELi6", "k_path_sm2<11 CTAs/SM, 6 visits per vote>   C5: 2M-triangle scene, quantised binary nodes from L2/HBM, path state parked in shared memory"),
     ("k_path_smILi0ELb0ELi8ELi6", "k_path_sm<LARGE, 8 CTAs/SM, 6 visits per vote>   the registers-only form of the same (tune[12] = 1)"),
     ("k_mega_path_regenILb1ELi0ELb0ELb0", "k_mega_path_regen<BVH, LARGE>   the while-while form of the same (tune[5] = 2)"),
     ("k_mega_path_regenILb1ELi2ELb0ELb1", "k_mega_path_regen<BVH, FLAT, COOP>    C4: Cornell box, flat leaf boxes, pooled triangle phase"),
