@@ -1497,7 +1497,11 @@ extern "C" int ptb_launch1d(ptb_device* dev, ptb_kernel* k, ptb_buffer* const* b
     k->ahead_w = res.x; k->ahead_h = res.y; std::memcpy(k->ahead_cfg, cfg, sizeof cfg);
     const bool speculate = k->frame_ahead != 0;
     if (speculate && !(k->ahead_count > 0 && z >= k->ahead_first && z < k->ahead_first + k->ahead_count) && k->streak >= 1) {
-        const long long target = (4ll << 20) << (dev->tune[1] > 0 && dev->tune[1] < 5 ? dev->tune[1] : 0);  // sample slots in flight (ptb_render's default; tune[1] = log2 multiplier for A/B runs)
+        // sample slots in flight: 16 Mi per device that shares the batch (this device + its helpers), so that a 2048x2048 frame loop
+        // still batches (round 2: with 4 Mi a 4 Mi-pixel frame was traced alone and eight GPUs gave nothing); tune[1] = log2 multiplier
+        int n_dev = 1;
+        for (ptb_device* hd : dev->helpers) n_dev += hd ? 1 : 0;
+        const long long target = ((16ll << 20) * n_dev) << (dev->tune[1] > 0 && dev->tune[1] < 5 ? dev->tune[1] : 0);
         int want = (int)((target + n_threads - 1) / n_threads);
         const int ramp = k->streak >= 5 ? want : (1 << k->streak);  // 2, 4, 8, 16 ... so a short sequence wastes little
         if (want > ramp) want = ramp;

@@ -6,6 +6,7 @@
 //   ptb_raycast [scene.bin] [out.ppm] [dimension=512] [frames=10000] [gpus=1 | PTB_GPUS]
 // gpus > 1: the other GPUs of the box become helpers of device 0 (DeviceUtils::Config::m_nGpus -> ptb_device_add_helper);
 // the loop below does not change and the image is bit-identical to one GPU.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -70,6 +71,7 @@ int main(int argc, char** argv) {
         DeviceUtils::waitForCompletion(m_d);
 
         // one launch per sample (:248-268)
+        const auto loop_t0 = std::chrono::steady_clock::now();
         unsigned frameCount = 0;
         while (frameCount != frames) {
             ptb_int4 res;
@@ -87,6 +89,7 @@ int main(int argc, char** argv) {
             launcher.launch1D(dimension * dimension);
             DeviceUtils::waitForCompletion(m_d);
         }
+        const double loop_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - loop_t0).count();
 
         // save the rendering (:270-290)
         if (rc == 0) {
@@ -106,7 +109,8 @@ int main(int argc, char** argv) {
                 std::fprintf(stderr, "writing %s failed: %s\n", path, ptb_last_error());
                 rc = 4;
             } else {
-                std::printf("%u frames of %dx%d on %d GPU(s) -> %s\n", frames, dimension, dimension, 1 + m_d->m_nHelpers, path);
+                std::printf("%u frames of %dx%d on %d GPU(s) -> %s   (launch loop %.3f s = %.4f ms per frame; device creation, scene upload and the PPM write are outside)\n",
+                            frames, dimension, dimension, 1 + m_d->m_nHelpers, path, loop_s, 1e3 * loop_s / (frames ? frames : 1));
             }
             DeviceUtils::waitForCompletion(m_d);
         }
