@@ -275,7 +275,8 @@ int ptb_device_counters(ptb_device* dev, int cumulative, ptb_counters* out);
  *  10 lanes waiting for the shade phase, 11 lanes at a leaf, that make the state-machine kernels switch phase (defaults 20 | 16, 10)
  *  12 large-scene PATH kernel: 1 = registers-only k_path_sm (8 CTAs per SM), 9 = the same at 9 CTAs; default k_path_sm2 (path state
  *     parked in shared memory, 11 CTAs), 28 | 29 | 30 = at 8 | 9 | 10 CTAs, 32 | 33 = 4 | 8 node visits per vote at 10 CTAs (default 6)
- *  13 = 1: wavefront extend in the while-while form for large scenes; = 2: FLAT scenes without the pooled triangle phase
+ *  13 = 1: wavefront extend stage as a state machine for large scenes (default: while-while with dynamic fetch); = 2: FLAT scenes
+ *     without the pooled triangle phase
  *  14 registers-only k_path_sm: 1 | 2 | 4 node visits per vote
  *  15 log2 of the sample slots kept in flight per launch (default 2^27 for PATH, 2^22 otherwise)                              */
 int ptb_device_set_tuning(ptb_device* dev, int index, int value);

@@ -287,7 +287,8 @@ def test_tessellated_scene_global_memory_path(dev, pt, ob, cornell, stack):
     try:
         _tessellated_body(dev, pt, ob, cornell)
     finally:
-        dev.set_tuning(2, 0)
+        for k in (2, 4, 13):
+            dev.set_tuning(k, 0)
 
 
 def _tessellated_body(dev, pt, ob, cornell):
@@ -304,7 +305,8 @@ def _tessellated_body(dev, pt, ob, cornell):
     assert_same_tree(nodes, order, ot)
     w, h = 64, 64
     for mode in (0, 1, 2, 3):
-        for integ in (pt.INTEGRATOR_MEGAKERNEL, pt.INTEGRATOR_WAVEFRONT):
+        for integ, t13 in ((pt.INTEGRATOR_MEGAKERNEL, 0), (pt.INTEGRATOR_WAVEFRONT, 0), (pt.INTEGRATOR_WAVEFRONT, 1)):  # tune[13] = 1: state-machine extend
+            dev.set_tuning(13, t13)
             prm = pt.default_params(width=w, height=h, n_frames=2, mode=mode, accum=pt.ACCUM_LINEAR, max_depth=6,
                                     collect_stats=1, integrator=integ, light_p1=p1, light_ea=ea, light_eb=eb)
             frame, stats = dev.buffer(w * h * 16), dev.buffer(w * h * 32)
@@ -323,6 +325,7 @@ def _tessellated_body(dev, pt, ob, cornell):
     for f in ("tri", "t", "u", "v"):
         np.testing.assert_array_equal(bits(g[f]), bits(r[f]))
     dev.set_tuning(4, 0)
+    dev.set_tuning(13, 0)
     sc.close()
 
 
