@@ -91,6 +91,10 @@ def oracle_small():
         bvh, _keep = ob.make_bvh(b["nodes"], b["tri_order"])
         out["bvh_nodes" + sfx] = b["nodes"].view(np.uint8).reshape(-1, b["nodes"].dtype.itemsize)
         out["bvh_order" + sfx] = b["tri_order"]
+        if width == 2:  # the quantised encoding the product traverses (ptb_bvh_nodeq) and its grid
+            q, lo, step = ob.quantize(b["nodes"])
+            out["bvh_qnodes_w2"] = q
+            out["bvh_qgrid_w2"] = np.array(lo + step, np.float32)
         for name, mode in (("primary", 0), ("ao", 1), ("direct", 2), ("path", 3)):
             prm = ob.default_params(32, 32, n_frames=3, mode=mode, accum=ob.ACCUM_LINEAR, use_bvh=1, max_depth=8,
                                     light_p1=p1, light_ea=ea, light_eb=eb)

@@ -154,6 +154,9 @@ def test_golden_vectors_on_device(dev, pt, cornell, width):
     assert sc.info()["width"] == width
     nodes, order = sc.bvh()
     assert nodes.view(np.uint8).tobytes() == g["bvh_nodes" + sfx].tobytes() and order.tolist() == g["bvh_order" + sfx].tolist()
+    if width == 2:  # the quantised encoding derived on the device equals the committed fixture
+        q, lo, step = sc.bvh_quantized()
+        assert q.tobytes() == g["bvh_qnodes_w2"].tobytes() and np.array(lo + step, np.float32).tobytes() == g["bvh_qgrid_w2"].tobytes()
     for name, mode in MODES.items():
         sfx = {1: "", 4: "_w4", 2: "_w2"}[sc.mode_width(mode)]  # a FLAT scene walks its 4-wide tree for DIRECT
         for integ in (pt.INTEGRATOR_MEGAKERNEL, pt.INTEGRATOR_WAVEFRONT):

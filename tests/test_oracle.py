@@ -257,6 +257,10 @@ def test_golden_small_renders(pt, ob, cornell, width):
     sfx = {1: "", 4: "_w4", 2: "_w2"}[width]
     b = ob.build_bvh(tris, width=width)
     assert b["nodes"].view(np.uint8).tobytes() == g["bvh_nodes" + sfx].tobytes()
+    if width == 2:  # the quantised encoding and its grid are pinned too
+        q, lo, step = ob.quantize(b["nodes"])
+        assert q.tobytes() == g["bvh_qnodes_w2"].tobytes()
+        assert np.array(lo + step, np.float32).tobytes() == g["bvh_qgrid_w2"].tobytes()
     np.testing.assert_array_equal(b["tri_order"], g["bvh_order" + sfx])
     pb = pt.build_bvh_host(tris, width=width)
     assert pb["nodes"].view(np.uint8).tobytes() == b["nodes"].view(np.uint8).tobytes() and np.array_equal(pb["tri_order"], b["tri_order"])
