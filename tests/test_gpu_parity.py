@@ -992,6 +992,13 @@ def test_render_multi_is_bit_identical(pt, ob, cornell, n_helpers):
         rgb, _ = main.render_multi(tris, mats, prm)
         lin, _, _ = single.render_host(tris, mats, pt.default_params(width=w, height=h, n_frames=4, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR, max_depth=5))
         np.testing.assert_array_equal(rgb, ob.to_rgb8(lin))
+        # a scene traversed from L2/HBM: every device gets the shared host-built tree and derives its own quantised nodes
+        big = pt.tessellate(tris, 12)
+        prm = pt.default_params(width=w, height=h, n_frames=2, mode=pt.MODE_PATH, accum=pt.ACCUM_LINEAR, max_depth=6)
+        got, ctr = main.render_multi(big, mats, prm)
+        want, _, wctr = single.render_host(big, mats, prm)
+        np.testing.assert_array_equal(bits(got), bits(want), err_msg="tessellated scene")
+        assert ctr["rays_closest"] == wctr["rays_closest"]
         # a changed scene is picked up by every device; an image with fewer blocks than devices still renders
         t2 = tris.copy()
         t2["p1"][10:12, 1] -= 0.5
