@@ -1,4 +1,4 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q -k "render_multi" > gpurun_out/gputest_v.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/gputest_v.log
+SWEEP_REPS=3 timeout 600 python tools/sweep_tune.py c4 32 "" "" 2>&1 | tee gpurun_out/sweep_c4_v.txt
